@@ -1,0 +1,160 @@
+/*
+ * pcompanion_b200 - C ABI of the B200-native P-Companion hot path.
+ *
+ * The reference (emreatilgan/P-Companion) has no FFI: its boundary is a set of PyTorch
+ * nn.Modules and a Python graph class.  This header is the boundary the
+ * Python host (the pcompanion_b200 package, which mirrors those classes) binds with ctypes.  Every
+ * entry point cites the reference code it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; sizes are element counts;
+ *   - `stream` is a cudaStream_t passed as void*; entry points enqueue work and return, they
+ *     never allocate, synchronise or keep state (workspace is supplied by the caller);
+ *   - return value: PC_OK or an error code; pc_last_error() gives the message (thread local);
+ *   - kernels are compiled for sm_100a only; there is no CPU fallback.
+ */
+#ifndef PCOMPANION_B200_H
+#define PCOMPANION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pc_stream_t;
+
+#define PC_OK 0
+#define PC_ERR_INVALID 1     /* bad argument (null pointer, unsupported size) */
+#define PC_ERR_CUDA 2        /* a CUDA runtime call failed */
+#define PC_ERR_WORKSPACE 3   /* workspace too small */
+#define PC_ERR_UNSUPPORTED 4 /* shape outside what the kernels are instantiated for */
+
+#define PC_ABI_VERSION 1
+
+int pc_abi_version(void);
+const char* pc_last_error(void);
+/* sm count / compute capability of the current device (host out-params). */
+int pc_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ------------------------------------------------------------------ (1) BPG -> CSR
+ * Replaces the Python dict/set graph of src/data/bpg.py:7-38 and the inline set algebra of
+ * src/data/synthetic_data.py:89-90,110-128.  An edge (src, dst) is the key src<<32 | dst, so
+ * ascending key order == (src, dst) order == CSR order. */
+
+/* keys[i] = src[i] << 32 | dst[i]        (bpg.py:19-22 add_edge, integer ids) */
+int pc_edge_keys_pack(const int32_t* src, const int32_t* dst, int64_t n, uint64_t* keys, pc_stream_t stream);
+/* inverse of pack */
+int pc_edge_keys_unpack(const uint64_t* keys, int64_t n, int32_t* src, int32_t* dst, pc_stream_t stream);
+
+/* LSD radix sort (8-bit digits) of 64-bit keys, ascending, result in `keys`.
+ * digit_mask bit d set => byte d of the key takes part (callers that know the id range skip
+ * the all-zero bytes).  Workspace: pc_sort_keys_workspace_bytes(n). */
+size_t pc_sort_keys_workspace_bytes(int64_t n);
+int pc_sort_keys(uint64_t* keys, int64_t n, uint32_t digit_mask, void* workspace, size_t workspace_bytes,
+                 pc_stream_t stream);
+
+/* Set semantics of edges[type].add(...) (bpg.py:21): drop adjacent duplicates of a sorted
+ * array.  *n_out (device int64) receives the count.  Workspace: pc_compact_workspace_bytes(n). */
+size_t pc_compact_workspace_bytes(int64_t n);
+int pc_unique_sorted_keys(const uint64_t* keys, int64_t n, uint64_t* out, int64_t* n_out, void* workspace,
+                          size_t workspace_bytes, pc_stream_t stream);
+
+/* Sorted-unique set algebra: out = { x in a : (x in b) == keep_if_present }.
+ * keep_if_present=1 -> a n b   (bpg.py:58-63, synthetic_data.py:89 "Bcv n Bpv")
+ * keep_if_present=0 -> a - b   (bpg.py:51-56, synthetic_data.py:89-90 "- Bcp", "- (Bpv u Bcv)") */
+int pc_set_filter_sorted(const uint64_t* a, int64_t na, const uint64_t* b, int64_t nb, int keep_if_present,
+                         uint64_t* out, int64_t* n_out, void* workspace, size_t workspace_bytes,
+                         pc_stream_t stream);
+
+/* Sorted-unique keys -> CSR: rowptr[r] = #keys with src < r, col[e] = dst of key e.
+ * Row i then lists get_neighbors(i, edge_type) in ascending order (bpg.py:24-31). */
+int pc_csr_from_sorted_keys(const uint64_t* keys, int64_t n_edges, int64_t n_rows, int64_t* rowptr, int32_t* col,
+                            pc_stream_t stream);
+
+/* keys_t[e] = col[e] << 32 | row(e): the transposed edge list (sort it and call
+ * pc_csr_from_sorted_keys to obtain the CSC used by the deterministic backward). */
+int pc_csr_transpose_keys(const int64_t* rowptr, const int32_t* col, int64_t n_rows, int64_t n_edges,
+                          uint64_t* keys_t, pc_stream_t stream);
+
+/* ------------------------------------------------------------------ (2) Product2Vec GAT
+ * Replaces the attention core of nn.MultiheadAttention as product2vec.py:24-29,60 calls it
+ * (need_weights branch: q*sqrt(1/dh), bmm, softmax, dropout, bmm) and its autograd
+ * (BmmBackward / SoftmaxBackward), over a CSR instead of zero-padded dense neighbours.
+ *
+ *   q      [n_dst, 128]  projected queries (NOT pre-scaled)
+ *   kv     [n_src, 256]  projected keys (cols 0..127) | values (cols 128..255)
+ *   rowptr [n_dst+1], col [E]: row i attends to kv[col[rowptr[i] .. rowptr[i+1])]
+ *   o      [n_dst, 128]  sum_j softmax_j(s_ij) v_j per head (before out_proj); 0 for empty rows
+ *   stats  [n_dst, 2, heads] fp32: [:,0,:] = log2-sum-exp of the scaled logits (written by fwd),
+ *                                  [:,1,:] = delta = dO.O per head (written by bwd_dst)
+ *   dropout_p in [0,1): attention-weight dropout (product2vec.py:27); the keep mask is a
+ *   counter-based hash of (seed, dst, src, head), regenerated in the backward kernels.
+ * embed dim is 128 (config.py:8); heads in {1,2,4,8}.  All three kernels are deterministic
+ * (fixed summation order per row, no float atomics). */
+int pc_gat_fwd(const float* q, const float* kv, const int64_t* rowptr, const int32_t* col, int64_t n_dst,
+               int heads, float dropout_p, uint64_t seed, float* o, float* stats, pc_stream_t stream);
+/* dst-major backward: dq [n_dst,128]; fills stats[:,1,:]. */
+int pc_gat_bwd_dst(const float* q, const float* kv, const int64_t* rowptr, const int32_t* col, int64_t n_dst,
+                   int heads, float dropout_p, uint64_t seed, const float* o, const float* d_o, float* stats,
+                   float* dq, pc_stream_t stream);
+/* src-major backward over the CSC (colptr [n_src+1], row [E] = dst ids per src, ascending):
+ * dkv [n_src, 256]. */
+int pc_gat_bwd_src(const float* q, const float* kv, const int64_t* colptr, const int32_t* row, int64_t n_src,
+                   int heads, float dropout_p, uint64_t seed, const float* d_o, const float* stats, float* dkv,
+                   pc_stream_t stream);
+
+/* ------------------------------------------------------------------ (3) hinge losses
+ * Row hinge:  per[r] = max(0, margin - ||a_r - p_g + eps|| + mean_k ||a_r - n_{g,k} + eps||),
+ * g = r / a_per_group, loss = mean_r per[r].
+ *   triplet (product2vec.py:137-154): a_per_group = 1, kneg = 5, eps = 1e-6 (F.pairwise_distance)
+ *   item    (p_companion.py:105-119):  a = proj[B*K,128], a_per_group = K, kneg = 1, eps = 0
+ * d_p / d_n may be NULL (required NULL when a_per_group > 1: positives are data there). */
+int pc_hinge_rows_fwd(const float* a, const float* p, const float* n, int64_t rows, int a_per_group, int kneg,
+                      int dim, float margin, float eps, float* per_row, float* loss, pc_stream_t stream);
+int pc_hinge_rows_bwd(const float* a, const float* p, const float* n, int64_t rows, int a_per_group, int kneg,
+                      int dim, float margin, float eps, const float* grad_loss, float* d_a, float* d_p, float* d_n,
+                      pc_stream_t stream);
+/* Type hinge (p_companion.py:95-103): per[i] = max(0, margin - S[i,pos_i] + S[i,neg_i]).
+ * bwd writes the two non-zeros of each row into a caller-zeroed d_sims. */
+int pc_hinge_type_fwd(const float* sims, const int64_t* pos, const int64_t* neg, int64_t rows, int64_t n_types,
+                      float margin, float* per_row, float* loss, pc_stream_t stream);
+int pc_hinge_type_bwd(const float* sims, const int64_t* pos, const int64_t* neg, int64_t rows, int64_t n_types,
+                      float margin, const float* grad_loss, float* d_sims, pc_stream_t stream);
+
+/* ------------------------------------------------------------------ (4) retrieval
+ * Replaces torch.matmul + torch.topk of p_companion.py:60-64, metrics.py:21,89 and the
+ * per-type filter -> matmul -> topk loop of inference.py:93-113.
+ * score[r,p] = sum_d double(q[r,d]) * double(c[p,d]) in the fixed "lane-blocked tree" order
+ * documented in oracle/retrieval.py; ranking = (score desc, index asc); padding = (-inf, -1).
+ *
+ * pc_topk_segments: every row scores the contiguous run members[seg_begin[r] .. seg_end[r])
+ * of catalog row ids (a type-sorted permutation from pc_sort_keys; or members == NULL for the
+ * identity, i.e. a plain slice of the catalog).  k <= 32, dim % 128 == 0. */
+size_t pc_topk_segments_workspace_bytes(int64_t rows, int k, int splits);
+int pc_topk_segments(const float* q, int64_t rows, int dim, const float* catalog, const int32_t* members,
+                     const int64_t* seg_begin, const int64_t* seg_end, int k, int splits, int64_t index_base,
+                     double* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                     pc_stream_t stream);
+/* Row-wise top-k of a materialised fp32 matrix [rows, cols] (torch.topk of p_companion.py:64 and
+ * metrics.py:21), same ranking rule; scores are returned as exact doubles of the inputs. */
+size_t pc_topk_rows_workspace_bytes(int64_t rows, int k, int splits);
+int pc_topk_rows(const float* values, int64_t rows, int64_t cols, int k, int splits, double* out_scores,
+                 int64_t* out_idx, void* workspace, size_t workspace_bytes, pc_stream_t stream);
+/* Merge `lists` candidate lists per row ([rows, lists*k] (score, idx), idx < 0 = padding) into the
+ * global top-k with ties -> lowest index (per-shard merge of SURVEY 8e; also the split merge). */
+int pc_topk_merge(const double* scores, const int64_t* idx, int64_t rows, int lists, int k, double* out_scores,
+                  int64_t* out_idx, pc_stream_t stream);
+
+/* ------------------------------------------------------------------ multi-GPU halo helpers
+ * Row gather (pack boundary K|V rows before the all-to-all) and deterministic scatter-add
+ * (owner-side reduction of returned dK|dV partials in fixed peer order). width in floats, %4==0. */
+int pc_rows_gather(const float* table, const int64_t* index, int64_t n, int width, float* out, pc_stream_t stream);
+int pc_rows_scatter_add(const float* rows, const int64_t* index, int64_t n, int width, float* table,
+                        pc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCOMPANION_B200_H */

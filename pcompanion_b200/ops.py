@@ -1,0 +1,338 @@
+"""Tensor-level wrappers and autograd Functions over the C ABI (include/pcompanion_b200.h).
+
+Everything here is thin: argument checks, output allocation (torch owns device memory), the
+current CUDA stream, one or a few native calls.  No arithmetic is done in PyTorch on this
+layer and nothing falls back to it.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, dev, stream
+
+I32, I64, F32, F64 = torch.int32, torch.int64, torch.float32, torch.float64
+EMB = 128  # embed dim the GAT kernels are instantiated for (reference config.py:8)
+
+
+# --------------------------------------------------------------------------- edge keys / sets
+def pack_keys(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """(src, dst) int32 -> int64 keys src<<32|dst (pc_edge_keys_pack; bpg.py:19-22)."""
+    if src.shape != dst.shape or src.dim() != 1:
+        raise ValueError("src and dst must be 1-D tensors of equal length")
+    keys = torch.empty(src.numel(), dtype=I64, device=src.device)
+    call("pc_edge_keys_pack", dev(src, I32, "src"), dev(dst, I32, "dst"), src.numel(), dev(keys, I64, "keys"), stream())
+    return keys
+
+
+def unpack_keys(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    src = torch.empty(keys.numel(), dtype=I32, device=keys.device)
+    dst = torch.empty_like(src)
+    call("pc_edge_keys_unpack", dev(keys, I64, "keys"), keys.numel(), dev(src, I32, "src"), dev(dst, I32, "dst"), stream())
+    return src, dst
+
+
+def digit_mask_for(num_ids: int) -> int:
+    """Bytes of a src<<32|dst key that can be non-zero when ids < num_ids."""
+    nbytes = max(1, ((max(int(num_ids), 2) - 1).bit_length() + 7) // 8)
+    low = (1 << nbytes) - 1
+    return low | (low << 4)
+
+
+def sort_keys_(keys: torch.Tensor, digit_mask: int = 0xFF) -> torch.Tensor:
+    """In-place ascending LSD radix sort (pc_sort_keys)."""
+    n = keys.numel()
+    ws = _lib.workspace(_lib.LIB.pc_sort_keys_workspace_bytes(n), keys.device)
+    call("pc_sort_keys", dev(keys, I64, "keys"), n, digit_mask, dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return keys
+
+
+def _compacted(out: torch.Tensor, n_out: torch.Tensor) -> torch.Tensor:
+    return out[: int(n_out.item())]  # one host sync: the output size is data dependent
+
+
+def unique_sorted(keys: torch.Tensor) -> torch.Tensor:
+    """Set semantics of edges[type].add (bpg.py:21) on a sorted key array."""
+    n = keys.numel()
+    out = torch.empty_like(keys)
+    n_out = torch.zeros(1, dtype=I64, device=keys.device)
+    ws = _lib.workspace(_lib.LIB.pc_compact_workspace_bytes(n), keys.device)
+    call("pc_unique_sorted_keys", dev(keys, I64, "keys"), n, dev(out, I64, "out"), dev(n_out, I64, "n_out"),
+         dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return _compacted(out, n_out)
+
+
+def set_filter(a: torch.Tensor, b: torch.Tensor, keep_if_present: bool) -> torch.Tensor:
+    """a n b (keep_if_present) or a - b on sorted-unique key arrays (pc_set_filter_sorted)."""
+    out = torch.empty_like(a)
+    n_out = torch.zeros(1, dtype=I64, device=a.device)
+    ws = _lib.workspace(_lib.LIB.pc_compact_workspace_bytes(a.numel()), a.device)
+    call("pc_set_filter_sorted", dev(a, I64, "a"), a.numel(), dev(b, I64, "b"), b.numel(), int(keep_if_present),
+         dev(out, I64, "out"), dev(n_out, I64, "n_out"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return _compacted(out, n_out)
+
+
+def set_intersection(a, b):
+    return set_filter(a, b, True)
+
+
+def set_difference(a, b):
+    return set_filter(a, b, False)
+
+
+def set_union(a: torch.Tensor, b: torch.Tensor, num_ids: int) -> torch.Tensor:
+    keys = torch.cat([a, b])
+    return unique_sorted(sort_keys_(keys, digit_mask_for(num_ids)))
+
+
+# --------------------------------------------------------------------------- CSR
+@dataclass
+class CSRGraph:
+    """Device CSR of one edge type: row i lists the ascending out-neighbours of node i
+    (== sorted(get_neighbors(i, edge_type)), bpg.py:24-31).  The transposed lists (CSC) needed
+    by the deterministic backward are built on first use."""
+    rowptr: torch.Tensor              # int64 [n_rows + 1]
+    col: torch.Tensor                 # int32 [E]
+    n_rows: int
+    n_cols: int
+    _t: Optional[Tuple[torch.Tensor, torch.Tensor]] = field(default=None, repr=False)
+
+    @property
+    def num_edges(self) -> int:
+        return self.col.numel()
+
+    def transposed(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(colptr int64 [n_cols+1], row int32 [E]): for every source j the ascending destinations."""
+        if self._t is None:
+            e = self.num_edges
+            keys_t = torch.empty(e, dtype=I64, device=self.col.device)
+            call("pc_csr_transpose_keys", dev(self.rowptr, I64, "rowptr"), dev(self.col, I32, "col"), self.n_rows, e,
+                 dev(keys_t, I64, "keys_t"), stream())
+            sort_keys_(keys_t, digit_mask_for(max(self.n_rows, self.n_cols)))
+            colptr, row = csr_from_sorted_keys(keys_t, self.n_cols)
+            self._t = (colptr, row)
+        return self._t
+
+
+def csr_from_sorted_keys(keys: torch.Tensor, n_rows: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    e = keys.numel()
+    rowptr = torch.empty(n_rows + 1, dtype=I64, device=keys.device)
+    col = torch.empty(e, dtype=I32, device=keys.device)
+    call("pc_csr_from_sorted_keys", dev(keys, I64, "keys"), e, n_rows, dev(rowptr, I64, "rowptr"), dev(col, I32, "col"), stream())
+    return rowptr, col
+
+
+def build_csr(src: torch.Tensor, dst: torch.Tensor, n_rows: int, n_cols: Optional[int] = None) -> Tuple[CSRGraph, torch.Tensor]:
+    """Edge list (duplicates allowed) -> (deduplicated CSRGraph, its sorted-unique keys)."""
+    n_cols = n_rows if n_cols is None else n_cols
+    keys = pack_keys(src, dst)
+    sort_keys_(keys, digit_mask_for(max(n_rows, n_cols)))
+    keys = unique_sorted(keys)
+    rowptr, col = csr_from_sorted_keys(keys, n_rows)
+    return CSRGraph(rowptr, col, n_rows, n_cols), keys
+
+
+_REGULAR_CACHE = {}
+
+
+def regular_graph(batch: int, n_nbr: int, device) -> CSRGraph:
+    """CSR of the dense drop-in path: row i attends to rows [i*n, (i+1)*n) of a [B*n, .] table -
+    the zero-padded [B, N, D] neighbour tensor of data_loader.py:186-198 viewed as a graph."""
+    key = (batch, n_nbr, str(device))
+    g = _REGULAR_CACHE.get(key)
+    if g is None:
+        e = batch * n_nbr
+        rowptr = torch.arange(batch + 1, dtype=I64, device=device) * n_nbr
+        col = torch.arange(e, dtype=I32, device=device)
+        colptr = torch.arange(e + 1, dtype=I64, device=device)
+        row = (torch.arange(e, dtype=I64, device=device) // max(n_nbr, 1)).to(I32)
+        g = CSRGraph(rowptr, col, batch, e, (colptr, row))
+        if len(_REGULAR_CACHE) > 64:
+            _REGULAR_CACHE.clear()
+        _REGULAR_CACHE[key] = g
+    return g
+
+
+# --------------------------------------------------------------------------- GAT
+class _GATAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, kv, graph: CSRGraph, heads: int, dropout_p: float, seed: int):
+        q = q.contiguous()
+        kv = kv.contiguous()
+        if q.dim() != 2 or q.shape[1] != EMB or kv.dim() != 2 or kv.shape[1] != 2 * EMB:
+            raise ValueError(f"gat: q must be [n_dst,{EMB}] and kv [n_src,{2 * EMB}], got {tuple(q.shape)}, {tuple(kv.shape)}")
+        if q.shape[0] != graph.n_rows or kv.shape[0] != graph.n_cols:
+            raise ValueError("gat: q / kv row counts do not match the graph")
+        o = torch.empty_like(q)
+        stats = torch.empty(q.shape[0], 2, heads, dtype=F32, device=q.device)
+        call("pc_gat_fwd", dev(q, F32, "q"), dev(kv, F32, "kv"), dev(graph.rowptr, I64, "rowptr"),
+             dev(graph.col, I32, "col"), graph.n_rows, heads, float(dropout_p), int(seed), dev(o, F32, "o"),
+             dev(stats, F32, "stats"), stream())
+        ctx.save_for_backward(q, kv, o, stats)
+        ctx.graph, ctx.heads, ctx.dropout_p, ctx.seed = graph, heads, float(dropout_p), int(seed)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, kv, o, stats = ctx.saved_tensors
+        g = ctx.graph
+        d_o = d_o.contiguous()
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        call("pc_gat_bwd_dst", dev(q, F32, "q"), dev(kv, F32, "kv"), dev(g.rowptr, I64, "rowptr"), dev(g.col, I32, "col"),
+             g.n_rows, ctx.heads, ctx.dropout_p, ctx.seed, dev(o, F32, "o"), dev(d_o, F32, "d_o"),
+             dev(stats, F32, "stats"), dev(dq, F32, "dq"), stream())
+        colptr, row = g.transposed()
+        call("pc_gat_bwd_src", dev(q, F32, "q"), dev(kv, F32, "kv"), dev(colptr, I64, "colptr"), dev(row, I32, "row"),
+             g.n_cols, ctx.heads, ctx.dropout_p, ctx.seed, dev(d_o, F32, "d_o"), dev(stats, F32, "stats"),
+             dev(dkv, F32, "dkv"), stream())
+        return dq, dkv, None, None, None, None
+
+
+def gat_attention(q: torch.Tensor, kv: torch.Tensor, graph: CSRGraph, heads: int, dropout_p: float = 0.0,
+                  seed: int = 0) -> torch.Tensor:
+    """o[i] = sum_j softmax_j(q_i.k_j / sqrt(dh)) v_j per head over the CSR (differentiable)."""
+    return _GATAttention.apply(q, kv, graph, heads, dropout_p, seed)
+
+
+# --------------------------------------------------------------------------- hinge losses
+class _HingeRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, p, n, a_per_group: int, kneg: int, margin: float, eps: float):
+        a, p, n = a.contiguous(), p.contiguous(), n.contiguous()
+        rows, dim = a.shape
+        per = torch.empty(rows, dtype=F32, device=a.device)
+        loss = torch.empty((), dtype=F32, device=a.device)
+        call("pc_hinge_rows_fwd", dev(a, F32, "a"), dev(p, F32, "p"), dev(n, F32, "n"), rows, a_per_group, kneg, dim,
+             margin, eps, dev(per, F32, "per"), dev(loss, F32, "loss"), stream())
+        ctx.save_for_backward(a, p, n)
+        ctx.cfg = (a_per_group, kneg, margin, eps)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        a, p, n = ctx.saved_tensors
+        a_per_group, kneg, margin, eps = ctx.cfg
+        rows, dim = a.shape
+        g = g.contiguous().to(F32)
+        da = torch.empty_like(a)
+        need_pn = a_per_group == 1 and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        dp = torch.empty_like(p) if need_pn else None
+        dn = torch.empty_like(n) if need_pn else None
+        call("pc_hinge_rows_bwd", dev(a, F32, "a"), dev(p, F32, "p"), dev(n, F32, "n"), rows, a_per_group, kneg, dim,
+             margin, eps, dev(g, F32, "grad"), dev(da, F32, "da"), dev(dp, F32, "dp"), dev(dn, F32, "dn"), stream())
+        return da, dp, dn, None, None, None, None
+
+
+def triplet_hinge(anchor, positive, negative, margin: float, eps: float = 1e-6) -> torch.Tensor:
+    """mean relu(margin - ||a-p+eps|| + mean_k ||a-n_k+eps||)  (product2vec.py:137-154)."""
+    if negative.dim() == 2:
+        negative = negative.unsqueeze(1)
+    b, k, d = negative.shape
+    return _HingeRows.apply(anchor, positive, negative.reshape(b * k, d), 1, k, float(margin), float(eps))
+
+
+def item_hinge(projected, positive_items, negative_items, margin: float) -> torch.Tensor:
+    """mean clamp(margin - ||proj-pos|| + ||proj-neg||, 0) over [B, K]  (p_companion.py:105-119)."""
+    b, k, d = projected.shape
+    return _HingeRows.apply(projected.reshape(b * k, d), positive_items, negative_items, k, 1, float(margin), 0.0)
+
+
+class _HingeType(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sims, pos, neg, margin: float):
+        sims = sims.contiguous()
+        pos, neg = pos.contiguous().to(I64), neg.contiguous().to(I64)
+        rows, nt = sims.shape
+        per = torch.empty(rows, dtype=F32, device=sims.device)
+        loss = torch.empty((), dtype=F32, device=sims.device)
+        call("pc_hinge_type_fwd", dev(sims, F32, "sims"), dev(pos, I64, "pos"), dev(neg, I64, "neg"), rows, nt, margin,
+             dev(per, F32, "per"), dev(loss, F32, "loss"), stream())
+        ctx.save_for_backward(sims, pos, neg)
+        ctx.margin = margin
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        sims, pos, neg = ctx.saved_tensors
+        rows, nt = sims.shape
+        d = torch.zeros_like(sims)
+        g = g.contiguous().to(F32)
+        call("pc_hinge_type_bwd", dev(sims, F32, "sims"), dev(pos, I64, "pos"), dev(neg, I64, "neg"), rows, nt,
+             ctx.margin, dev(g, F32, "grad"), dev(d, F32, "d_sims"), stream())
+        return d, None, None, None
+
+
+def type_hinge(sims, pos, neg, margin: float) -> torch.Tensor:
+    """mean clamp(margin - S[i,pos_i] + S[i,neg_i], 0)  (p_companion.py:95-103)."""
+    return _HingeType.apply(sims, pos, neg, float(margin))
+
+
+# --------------------------------------------------------------------------- retrieval
+def _auto_splits(rows: int, avg_len: float) -> int:
+    sms = 148
+    if rows >= 2 * sms:
+        return 1
+    want = max(1, (2 * sms + rows - 1) // max(rows, 1))
+    cap = max(1, int(avg_len // 256))
+    return max(1, min(want, cap, 1024))
+
+
+def topk_segments(q: torch.Tensor, catalog: torch.Tensor, seg_begin: torch.Tensor, seg_end: torch.Tensor, k: int,
+                  members: Optional[torch.Tensor] = None, index_base: int = 0, splits: Optional[int] = None):
+    """Exact top-k of every row over its run of catalog rows; returns (scores f64 [R,k], idx i64 [R,k])."""
+    rows, dim = q.shape
+    if splits is None:
+        avg = float((seg_end - seg_begin).float().mean().item()) if rows else 0.0
+        splits = _auto_splits(rows, avg)
+    out_s = torch.empty(rows, k, dtype=F64, device=q.device)
+    out_i = torch.empty(rows, k, dtype=I64, device=q.device)
+    ws = _lib.workspace(_lib.LIB.pc_topk_segments_workspace_bytes(rows, k, splits), q.device)
+    call("pc_topk_segments", dev(q.contiguous(), F32, "q"), rows, dim, dev(catalog, F32, "catalog"),
+         dev(members, I32, "members"), dev(seg_begin, I64, "seg_begin"), dev(seg_end, I64, "seg_end"), k, splits,
+         int(index_base), dev(out_s, F64, "out_scores"), dev(out_i, I64, "out_idx"), dev(ws, torch.uint8, "ws"),
+         ws.numel(), stream())
+    return out_s, out_i
+
+
+def topk_rows(values: torch.Tensor, k: int, splits: Optional[int] = None):
+    """Row-wise top-k of a materialised fp32 matrix, ties -> lowest index (torch.topk replacement)."""
+    values = values.contiguous()
+    rows, cols = values.shape
+    if splits is None:
+        splits = _auto_splits(rows, float(cols))
+    out_s = torch.empty(rows, k, dtype=F64, device=values.device)
+    out_i = torch.empty(rows, k, dtype=I64, device=values.device)
+    ws = _lib.workspace(_lib.LIB.pc_topk_rows_workspace_bytes(rows, k, splits), values.device)
+    call("pc_topk_rows", dev(values, F32, "values"), rows, cols, k, splits, dev(out_s, F64, "out_scores"),
+         dev(out_i, I64, "out_idx"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return out_s, out_i
+
+
+def topk_merge(scores: torch.Tensor, idx: torch.Tensor, k: int):
+    """Merge [R, lists*k] candidates -> [R, k] (per-shard merge)."""
+    rows, total = scores.shape
+    lists = total // k
+    out_s = torch.empty(rows, k, dtype=F64, device=scores.device)
+    out_i = torch.empty(rows, k, dtype=I64, device=scores.device)
+    call("pc_topk_merge", dev(scores.contiguous(), F64, "scores"), dev(idx.contiguous(), I64, "idx"), rows, lists, k,
+         dev(out_s, F64, "out_scores"), dev(out_i, I64, "out_idx"), stream())
+    return out_s, out_i
+
+
+# --------------------------------------------------------------------------- halo helpers
+def rows_gather(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(index.numel(), table.shape[1], dtype=F32, device=table.device)
+    call("pc_rows_gather", dev(table, F32, "table"), dev(index, I64, "index"), index.numel(), table.shape[1],
+         dev(out, F32, "out"), stream())
+    return out
+
+
+def rows_scatter_add_(table: torch.Tensor, index: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """table[index] += rows; `index` must hold unique ids (deterministic, no atomics)."""
+    call("pc_rows_scatter_add", dev(rows.contiguous(), F32, "rows"), dev(index, I64, "index"), index.numel(),
+         table.shape[1], dev(table, F32, "table"), stream())
+    return table
