@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""Benchmark of the P-Companion hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload gat|retrieval]
+
+Default workload = BASELINE.json configs[1]: synthetic BPG with 1 M products / ~20 M co-view
+edges per GPU, one step = full-graph Product2Vec GAT forward + triplet hinge + backward + Adam
+(every destination, every edge, per-node FFN / QKV / out-proj included).  Metric: co-view edges
+processed per second, whole job.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from types import SimpleNamespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NODES_PER_GPU = 1_000_000
+EDGES_PER_GPU = 20_000_000
+TRIPLETS = 131_072
+KNEG = 5
+SEED = 1234
+
+# algorithmic bytes of the three sparse kernels (fp32, per edge / per node)
+ALGO_BYTES = {
+    "pc_gat_fwd": (1028, 1060),
+    "pc_gat_bwd_dst": (1060, 1588),
+    "pc_gat_bwd_src": (1064, 1028),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        out = self.proc.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_cfg(device):
+    # reference config.py:8-24 defaults (DROPOUT = 0.1 stays on: attention dropout is part of a training step)
+    return SimpleNamespace(PRODUCT_EMB_DIM=128, TYPE_EMB_DIM=64, HIDDEN_SIZE=256, NUM_ATTENTION_HEADS=4, DROPOUT=0.1,
+                           MARGIN=1.0, ALPHA=0.8, NUM_COMP_TYPES=3, NUM_TYPES=34800, LEARNING_RATE=1e-3, DEVICE=device)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import pcompanion_b200 as pc
+    from pcompanion_b200 import _lib, ops
+    from pcompanion_b200.synthetic import synthetic_bpg
+
+    if args.workload == "retrieval":
+        return run_retrieval(args, rank, world, dev)
+    if world > 1:
+        from pcompanion_b200.distributed import run_partitioned_bench
+        return run_partitioned_bench(args, rank, world, dev)
+
+    torch.manual_seed(SEED)
+    t0 = time.perf_counter()
+    bpg = synthetic_bpg(NODES_PER_GPU, EDGES_PER_GPU, seed=SEED, device=dev)
+    graph = bpg.csr("co_view")
+    graph.transposed()
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    n, e = graph.n_rows, graph.num_edges
+    cfg = make_cfg(dev)
+    model = pc.Product2Vec(cfg).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+    g = torch.Generator(device=dev).manual_seed(SEED + 2)
+    trip = torch.randint(0, n, (TRIPLETS, 2 + KNEG), generator=g, device=dev)
+    x_dev = bpg.features
+    # host copies for the end-to-end leg (pinned)
+    x_host = x_dev.cpu().pin_memory()
+    trip_host = trip.cpu().pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(x, tr):
+        emb = model.forward_graph(x, graph)
+        a, p = emb[tr[:, 0]], emb[tr[:, 1]]
+        ng = emb[tr[:, 2:].reshape(-1)].reshape(TRIPLETS, KNEG, -1)
+        loss = model.triplet_loss(a, p, ng)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        x = torch.empty_like(x_dev); x.copy_(x_host, non_blocking=True)
+        tr = torch.empty_like(trip); tr.copy_(trip_host, non_blocking=True)
+        loss = step(x, tr)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+
+    for _ in range(args.warmup):
+        step(x_dev, trip)
+    torch.cuda.synchronize()
+
+    # ---- device-resident timed region (per-kernel events on the launching stream)
+    sampler = ClockSampler(local)
+    _lib.PROFILE = []
+    launches0 = _lib.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev, trip)
+    ev1.record()
+    torch.cuda.synchronize()
+    total_ms = ev0.elapsed_time(ev1)
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    launches = _lib.LAUNCHES - launches0
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+
+    per_kernel = {}
+    for name, s, t in prof:
+        per_kernel.setdefault(name, []).append(s.elapsed_time(t))
+    peak, peak_src = measured_peaks()
+    kernels = {}
+    for name, (be, bn) in ALGO_BYTES.items():
+        if name in per_kernel:
+            ms = sum(per_kernel[name]) / len(per_kernel[name])
+            gbs = (be * e + bn * n) / (ms * 1e-3) / 1e9
+            kernels[name] = {"ms": round(ms, 4), "algo_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    sparse_ms = sum(k["ms"] for k in kernels.values())
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algo_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "sparse_fwd_bwd": {"ms": round(sparse_ms, 4),
+                                   "algo_gbs": round((3152 * e + 3676 * n) / (sparse_ms * 1e-3) / 1e9, 1),
+                                   "frac": round((3152 * e + 3676 * n) / (sparse_ms * 1e-3) / 1e9 / peak, 4)},
+                "kernels": kernels}
+
+    # ---- end-to-end leg: host buffers, H2D + D2H inside the timed region
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1) / args.steps
+
+    cpu = cpu_baseline_gat(bpg, graph, cfg, seconds=15.0)
+    line = {
+        "metric": "gat_edges_per_sec_fwd_bwd", "value": e / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: synthetic BPG 1M products / 20M co-view edges, Product2Vec full-graph GAT fwd+bwd "
+                               "(FFN+QKV+out-proj per node, triplet hinge on 131072 triplets, Adam), 1xB200",
+                   "nodes": n, "edges": e, "heads": 4, "dropout": cfg.DROPOUT, "triplets": TRIPLETS,
+                   "l2": "working set (K|V 1 GB, Q 0.5 GB) exceeds the 126 MB L2; no flush needed",
+                   "csr_build_s": round(build_s, 3)},
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": {"value": e / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": x_host.numel() * 4 + trip_host.numel() * 8, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "loss": float(loss.item()),
+    }
+    print(json.dumps(line))
+
+
+def run_retrieval(args, rank, world, dev):
+    """C4: masked top-10 over a 10 M-product catalog (sharded over the ranks), 1 K types, Q queries x 3 type rows."""
+    import torch.distributed as dist
+    import pcompanion_b200 as pc
+    from pcompanion_b200 import _lib
+    p_total, n_types, q_n, k = 10_000_000, 1000, args.queries, 10
+    per = p_total // world
+    base = rank * per
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    catalog = torch.randn(per, 128, generator=g, device=dev)
+    type_id = torch.randint(0, n_types, (per,), generator=g, device=dev, dtype=torch.int32)
+    cat = pc.ShardedCatalog(catalog, type_id, base, n_types)
+    gq = torch.Generator(device=dev).manual_seed(SEED)
+    queries = torch.randn(q_n * 3, 128, generator=gq, device=dev)
+    row_type = torch.randint(0, n_types, (q_n * 3,), generator=gq, device=dev, dtype=torch.int32)
+    q_host, t_host = queries.cpu().pin_memory(), row_type.cpu().pin_memory()
+    for _ in range(args.warmup):
+        cat.topk(queries, k, row_type)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(dev.index)
+    launches0 = _lib.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        s, i = cat.topk(queries, k, row_type)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = _lib.LAUNCHES - launches0
+    clocks = sampler.stop()
+    ev0.record()
+    for _ in range(args.steps):
+        qd = torch.empty_like(queries); qd.copy_(q_host, non_blocking=True)
+        td = torch.empty_like(row_type); td.copy_(t_host, non_blocking=True)
+        s, i = cat.topk(qd, k, td)
+        i_host = i.cpu()
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1) / args.steps
+    t = torch.tensor([ms, e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        scored = q_n * 3 * (p_total / n_types)          # (row, product) pairs actually scored
+        bytes_read = scored * 512
+        line = {"metric": "topk_queries_per_sec", "value": q_n / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C4: top-10 over 10M-product catalog, 1K types, {q_n} queries x 3 type rows, "
+                                       f"catalog sharded over {world} GPU(s), type-segmented exact fp64 scoring"},
+                "roofline": {"bound": "hbm", "achieved": bytes_read / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": bytes_read / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "note": "algorithmic bytes = 512 B per (row, product of the row's type) pair"},
+                "clocks": clocks,
+                "e2e": {"value": q_n / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": q_host.numel() * 4 + t_host.numel() * 4,
+                        "d2h_bytes_per_step": q_n * 3 * k * 8},
+                "gpu_launches": launches}
+        print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- CPU baseline / reference arm
+def padded_batches(graph_rowptr, graph_col, feats, n_batches, batch, gen):
+    """Index-based collate (no Python sets): dense zero-padded neighbour tensors exactly as
+    data_loader.py:171-206 would build them for `batch` destinations."""
+    n = graph_rowptr.numel() - 1
+    for _ in range(n_batches):
+        rows = torch.randint(0, n, (batch,), generator=gen)
+        lo, hi = graph_rowptr[rows], graph_rowptr[rows + 1]
+        deg = hi - lo
+        nmax = int(deg.max().item())
+        ar = torch.arange(max(nmax, 1)).unsqueeze(0)
+        mask = ar < deg.unsqueeze(1)
+        idx = (lo.unsqueeze(1) + ar).clamp_(max=graph_col.numel() - 1)
+        nbr_ids = graph_col[idx].long()
+        nbrs = feats[nbr_ids] * mask.unsqueeze(-1)
+        yield {"anchor": feats[rows], "positive": feats[torch.randint(0, n, (batch,), generator=gen)],
+               "negative": feats[torch.randint(0, n, (batch * KNEG,), generator=gen)].reshape(batch, KNEG, -1),
+               "anchor_neighbors": nbrs}, int(deg.sum().item()), batch * max(nmax, 1)
+
+
+def cpu_gat_sample(feats, rowptr, col, cfg, seconds, batch=4096, max_batches=64):
+    from oracle import torch_port
+    torch.manual_seed(SEED)
+    model = torch_port.PortProduct2Vec(torch_port.default_config(DROPOUT=cfg.DROPOUT)).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    gen = torch.Generator().manual_seed(SEED)
+    real = padded = nb = 0
+    # one untimed batch to warm the allocator / thread pool
+    for b, _, _ in padded_batches(rowptr, col, feats, 1, batch, gen):
+        torch_port.port_triplet_loss(model, b, cfg.MARGIN).backward()
+    t0 = time.perf_counter()
+    for b, r, p in padded_batches(rowptr, col, feats, max_batches, batch, gen):
+        loss = torch_port.port_triplet_loss(model, b, cfg.MARGIN)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        real += r; padded += p; nb += 1
+        if time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    return real, padded, nb, dt
+
+
+def cpu_baseline_gat(bpg, graph, cfg, seconds):
+    feats = bpg.features.cpu()
+    rowptr, col = graph.rowptr.cpu(), graph.col.cpu()
+    real, padded, nb, dt = cpu_gat_sample(feats, rowptr, col, cfg, seconds)
+    return {"value": padded / dt, "unit": "edges/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(),
+            "kind": "port",
+            "sample": f"{nb} batches x 4096 destinations of the same C2 graph through the torch-CPU port of the reference "
+                      f"Product2Vec (zero-padded neighbour lists, FFN per edge row, fwd+bwd+Adam); value counts padded "
+                      f"edges ({padded}), real edges {real} -> {real / dt:.0f} real edges/s; {dt:.1f} s"}
+
+
+def run_reference(args):
+    """The reference's own CPU path (torch-CPU port in oracle/torch_port.py; the reference is pure
+    Python/PyTorch and cannot travel to the GPU box) on the host cores, same workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cfg = make_cfg(torch.device("cpu"))
+    if args.workload == "retrieval":
+        from oracle import torch_port
+        g = torch.Generator().manual_seed(SEED)
+        p_sample, n_types, k = 1_000_000, 1000, 10
+        catalog = torch.randn(p_sample, 128, generator=g)
+        type_id = torch.randint(0, n_types, (p_sample,), generator=g)
+        rows = 96
+        q = torch.randn(rows, 128, generator=g)
+        rt = torch.randint(0, n_types, (rows,), generator=g)
+        for _ in range(args.warmup):
+            torch_port.port_dense_topk(q, catalog, rt, type_id, k)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            torch_port.port_dense_topk(q, catalog, rt, type_id, k)
+        dt = (time.perf_counter() - t0) / args.steps
+        qps = rows / 3 / dt / 10.0   # 1 M-row sample, scaled linearly to the 10 M catalog
+        line = {"impl": "reference", "metric": "topk_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C4 sample: torch matmul + type mask + topk(10), 96 rows x 1M-product sample, scaled x1/10 to 10M"},
+                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": "96 score rows x 1M products per step, dense fp32 matmul+mask+topk"},
+                "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    # GAT: destinations of a C2-like graph (uniform random neighbours, Poisson(20) degrees); the CPU sample only
+    # needs the local structure of the graph, not the 20 M-edge CSR
+    gen = torch.Generator().manual_seed(SEED)
+    n = NODES_PER_GPU
+    per_step_batches = 2
+    feats = torch.randn(n, 128, generator=gen)
+    from oracle import torch_port
+    model = torch_port.PortProduct2Vec(torch_port.default_config(DROPOUT=cfg.DROPOUT)).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    # neighbour lists are drawn at the C2 degree (mean 20): repeat-sample columns per destination
+    def batches(k):
+        for _ in range(k):
+            rows = torch.randint(0, n, (4096,), generator=gen)
+            deg = torch.poisson(torch.full((4096,), EDGES_PER_GPU / NODES_PER_GPU), generator=gen).long().clamp_(min=0)
+            nmax = int(deg.max().item())
+            nbr = torch.randint(0, n, (4096, nmax), generator=gen)
+            mask = torch.arange(nmax).unsqueeze(0) < deg.unsqueeze(1)
+            yield {"anchor": feats[rows], "positive": feats[torch.randint(0, n, (4096,), generator=gen)],
+                   "negative": feats[torch.randint(0, n, (4096 * KNEG,), generator=gen)].reshape(4096, KNEG, -1),
+                   "anchor_neighbors": feats[nbr] * mask.unsqueeze(-1)}, int(deg.sum()), 4096 * nmax
+
+    def one_step():
+        real = padded = 0
+        for bt, r, p in batches(per_step_batches):
+            loss = torch_port.port_triplet_loss(model, bt, cfg.MARGIN)
+            opt.zero_grad(); loss.backward(); opt.step()
+            real += r; padded += p
+        return real, padded
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    real = padded = 0
+    for _ in range(args.steps):
+        r, p = one_step()
+        real += r; padded += p
+    dt = time.perf_counter() - t0
+    val = padded / dt
+    line = {"impl": "reference", "metric": "gat_edges_per_sec_fwd_bwd", "value": val, "unit": "edges/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 sample: reference Product2Vec (torch-CPU port) fwd+bwd+Adam on 2 x 4096-destination padded "
+                                   "batches per step, neighbour lists at the C2 degree distribution (Poisson mean 20)"},
+            "cpu_baseline": {"value": val, "unit": "edges/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(),
+                             "kind": "port", "sample": f"{args.steps} steps x 2 batches x 4096 destinations; padded edges {padded}, "
+                                                       f"real edges {real} ({real / dt:.0f} real edges/s)"},
+            "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gat", choices=["gat", "retrieval"])
+    ap.add_argument("--queries", type=int, default=4096)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

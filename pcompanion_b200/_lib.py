@@ -71,6 +71,7 @@ def _load() -> ctypes.CDLL:
 
 LIB = _load()
 LAUNCHES = 0  # number of C-ABI compute entry points invoked (bench.py reports kernels launched)
+PROFILE = None  # when a list: (name, start_event, end_event) per native call, for bench.py's per-kernel timing
 
 
 def check(rc: int) -> None:
@@ -81,7 +82,14 @@ def check(rc: int) -> None:
 def call(name: str, *args) -> None:
     global LAUNCHES
     LAUNCHES += 1
+    if PROFILE is None:
+        check(getattr(LIB, name)(*args))
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
     check(getattr(LIB, name)(*args))
+    end.record()
+    PROFILE.append((name, start, end))
 
 
 def stream() -> c_void_p:

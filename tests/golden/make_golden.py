@@ -95,7 +95,7 @@ def golden_p2v_module():
     out["train_negative_emb"] = n.detach().numpy()
     out["train_loss"] = loss.detach().numpy()
     for k, v in m.named_parameters():
-        out["grad/" + k] = v.grad.numpy()
+        out["grad/" + k] = v.grad.numpy().copy()
     out["train_running_mean"] = m.ffn[1].running_mean.numpy().copy()
     out["train_running_var"] = m.ffn[1].running_var.numpy().copy()
     out["train_num_batches_tracked"] = m.ffn[1].num_batches_tracked.numpy().copy()
@@ -107,7 +107,7 @@ def golden_p2v_module():
     o = m.apply_attention(q, kv)
     (o * w).sum().backward()
     out.update(attn_q=q.detach().numpy(), attn_kv=kv.detach().numpy(), attn_w=w.numpy(),
-               attn_out=o.detach().numpy(), attn_dq=q.grad.numpy(), attn_dkv=kv.grad.numpy())
+               attn_out=o.detach().numpy(), attn_dq=q.grad.numpy().copy(), attn_dkv=kv.grad.numpy().copy())
     np.savez_compressed(os.path.join(HERE, "p2v_module.npz"), **out)
 
 
@@ -210,7 +210,7 @@ def golden_pcomp():
                                             batch["negative_items"]).detach().numpy()
     for k, v in m.named_parameters():
         if v.grad is not None:
-            out["grad/" + k] = v.grad.numpy()
+            out["grad/" + k] = v.grad.numpy().copy()
     # evaluate_model-style in-batch scoring, metrics.py:89-100
     from src.utils.metrics import Metrics
     sims = torch.matmul(o["projected_embeddings"].detach().view(-1, 128), batch["target_features"].T)

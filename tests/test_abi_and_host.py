@@ -1,0 +1,129 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the
+ctypes prototypes cover the header, the host classes keep the reference's surface and refuse to
+run without CUDA (no compute is launched here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden, state_dict_from
+
+HEADER = os.path.join(ROOT, "include", "pcompanion_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from pcompanion_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pcompanion_b200.h but not exported"
+    assert lib.pc_abi_version() == 1
+
+
+def test_ctypes_prototypes_cover_the_header_exactly():
+    from pcompanion_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == header_functions()
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _lib.PROTOTYPES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*)\)\s*;", src, flags=re.S)
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), f"{name}: header has {len(params)} parameters, ctypes binding {len(args)}"
+
+
+def test_workspace_queries_need_no_gpu():
+    from pcompanion_b200 import _lib
+    assert _lib.LIB.pc_sort_keys_workspace_bytes(0) == 0
+    assert _lib.LIB.pc_sort_keys_workspace_bytes(1_000_000) >= 8_000_000
+    assert _lib.LIB.pc_compact_workspace_bytes(1_000_000) >= 8_000_000
+    assert _lib.LIB.pc_topk_segments_workspace_bytes(10, 10, 1) == 0
+    assert _lib.LIB.pc_topk_segments_workspace_bytes(10, 10, 4) == 10 * 4 * 10 * 16
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from pcompanion_b200 import _lib
+    rc = _lib.LIB.pc_gat_fwd(None, None, None, None, 5, 3, 0.0, 0, None, None, None)
+    assert rc != 0 and b"gat" in _lib.LIB.pc_last_error()
+    with pytest.raises(RuntimeError, match="native call failed"):
+        _lib.check(rc)
+    assert _lib.LIB.pc_topk_merge(None, None, 4, 2, 64, None, None, None) != 0
+
+
+def make_cfg(**over):
+    from types import SimpleNamespace
+    cfg = SimpleNamespace(PRODUCT_EMB_DIM=128, TYPE_EMB_DIM=64, HIDDEN_SIZE=256, NUM_ATTENTION_HEADS=4, DROPOUT=0.1,
+                          MARGIN=1.0, ALPHA=0.8, NUM_COMP_TYPES=3, NUM_TYPES=40, DEVICE=torch.device("cpu"))
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def test_state_dict_layout_equals_the_reference():
+    """Keys and shapes of the reference checkpoints (golden state_dicts come from the real modules)."""
+    from pcompanion_b200 import PCompanion, Product2Vec
+    g = load_golden("p2v_module.npz")
+    ref = state_dict_from(g)
+    m = Product2Vec(make_cfg())
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(tuple(sd[k].shape) == ref[k].shape for k in ref)
+    m.load_state_dict({k: torch.tensor(v) for k, v in ref.items()})
+    gp = load_golden("pcomp.npz")
+    refp = state_dict_from(gp)
+    pm = PCompanion(make_cfg(), {f"P{i}": torch.zeros(128) for i in range(refp["product_embeddings.weight"].shape[0])})
+    assert set(pm.state_dict().keys()) == set(refp.keys())
+    assert all(tuple(pm.state_dict()[k].shape) == refp[k].shape for k in refp)
+    assert not pm.product_embeddings.weight.requires_grad          # frozen, p_companion.py:26-29
+    assert pm.product_to_idx["P3"] == 3
+
+
+def test_same_seed_gives_the_reference_initialisation():
+    """Same construction order as product2vec.py:14-29 -> torch.manual_seed(s) reproduces the
+    reference's initial weights (the golden state_dict was drawn with seed 0 before BN edits)."""
+    from pcompanion_b200 import Product2Vec
+    g = load_golden("p2v_module.npz")
+    torch.manual_seed(0)
+    m = Product2Vec(make_cfg())
+    for k in ("ffn.0.weight", "ffn.5.bias", "attention.in_proj_weight", "attention.out_proj.weight"):
+        assert np.array_equal(m.state_dict()[k].numpy(), g["sd/" + k]), k
+
+
+def test_cpu_inputs_are_refused_not_silently_computed():
+    from pcompanion_b200 import PCompanion, Product2Vec, ops
+    m = Product2Vec(make_cfg())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(4, 128))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.get_initial_embedding(torch.zeros(128))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.pack_keys(torch.zeros(3, dtype=torch.int32), torch.zeros(3, dtype=torch.int32))
+    pm = PCompanion(make_cfg(), torch.zeros(10, 128))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pm({"query_ids": torch.zeros(2, dtype=torch.int64), "query_types": torch.zeros(2, dtype=torch.int64)})
+
+
+def test_digit_mask_and_bpg_surface_without_device_work():
+    from pcompanion_b200 import BehaviorProductGraph, ops
+    assert ops.digit_mask_for(2) == 0x11 and ops.digit_mask_for(256) == 0x11 and ops.digit_mask_for(257) == 0x33
+    assert ops.digit_mask_for(1_000_000) == 0x77 and ops.digit_mask_for(1 << 31) == 0xFF
+    b = BehaviorProductGraph()
+    b.add_node("a", {"type": "t0"}); b.add_node("b", {"type": "t1"})
+    b.add_edge("a", "b", "co_view"); b.add_edge("a", "b", "co_view"); b.add_edge("a", "b", "nonsense")
+    assert b.edges["co_view"] == {("a", "b")} and set(b.edges) == {"co_purchase", "co_view", "purchase_after_view"}
+    assert b.get_all_types() == {"t0", "t1"}
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from pcompanion_b200 import _lib
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.NativeLibraryError, match="no CPU or PyTorch fallback"):
+        _lib._load()
