@@ -195,7 +195,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
 
-    cpu = cpu_baseline_gat(bpg, graph, cfg, seconds=15.0)
+    cpu = None if args.skip_cpu else cpu_baseline_gat(bpg, graph, cfg, seconds=15.0)
     line = {
         "metric": "gat_edges_per_sec_fwd_bwd", "value": e / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -420,6 +420,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gat", choices=["gat", "retrieval"])
     ap.add_argument("--queries", type=int, default=4096)
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -105,6 +105,19 @@ int pc_gat_bwd_src(const float* q, const float* kv, const int64_t* colptr, const
                    int heads, float dropout_p, uint64_t seed, const float* d_o, const float* stats, float* dkv,
                    pc_stream_t stream);
 
+/* Dense row projection on the tensor cores (tcgen05, 3xTF32 split => fp32-faithful, see gemm.cu):
+ *   Y[m, n] = epilogue( A[m, k] . W[n, k]^T + bias[n] )
+ * Replaces the addmm behind nn.Linear (product2vec.py:14-21), the packed in-/out-projection of
+ * nn.MultiheadAttention (:24-29, :60) and, on the transposed weight, their dgrad GEMMs.
+ * A row-major with leading dimension lda; W row-major [n, k] (nn.Linear layout); k % 32 == 0,
+ * n % 32 == 0, n <= 768.  Columns [0, split) go to out0 (ld0), [split, n) to out1 (ld1) - the
+ * Q | K|V outputs of the packed in-projection.  epilogue: 0 bias, 1 tanh(. + bias),
+ * 2 (. + bias) * (1 - aux^2) (gradient through tanh, aux = tanh output),
+ * 3 row r keeps (. + bias) if rowptr[r+1] > rowptr[r] else takes aux[r, :] (product2vec.py:76). */
+int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, const float* bias,
+                     int epilogue, const float* aux, int64_t ld_aux, const int64_t* rowptr, float* out0, int64_t ld0,
+                     int split, float* out1, int64_t ld1, pc_stream_t stream);
+
 /* ------------------------------------------------------------------ (3) hinge losses
  * Row hinge:  per[r] = max(0, margin - ||a_r - p_g + eps|| + mean_k ||a_r - n_{g,k} + eps||),
  * g = r / a_per_group, loss = mean_r per[r].

@@ -17,7 +17,7 @@ def run() -> None:
     torch.manual_seed(0)
     cfg = SimpleNamespace(PRODUCT_EMB_DIM=128, HIDDEN_SIZE=256, NUM_ATTENTION_HEADS=4, DROPOUT=0.0, MARGIN=1.0,
                           DEVICE=dev)
-    n, e = 300, 2500
+    n, e = 600, 5000
     src = torch.randint(0, n, (e,), dtype=torch.int32)
     dst = torch.randint(0, n, (e,), dtype=torch.int32)
     feats = torch.randn(n, 128)

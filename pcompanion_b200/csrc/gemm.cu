@@ -1,0 +1,374 @@
+// Dense row projections on the 5th-generation tensor cores: Y = epi(A . W^T + bias), fp32-faithful.
+//
+// Replaces the addmm calls behind nn.Linear in /root/reference/src/models/product2vec.py:14-21
+// (FFN), the packed in-projection / out-projection of nn.MultiheadAttention (:24-29, :60) and
+// their autograd dgrad GEMMs (dX = dY . W, run as the same kernel on the transposed weight).
+//
+// Precision: the reference computes these GEMMs in fp32 and BASELINE.json asks for 1e-5 relative
+// parity, which single-pass TF32/BF16 tensor-core math (~1e-3) cannot give.  Each operand is
+// therefore split on the fly into hi = rn_tf32(x) and lo = x - hi, and three tcgen05.mma
+// (kind::tf32, fp32 accumulation in TMEM) are issued per K step: lo.hi + hi.lo + hi.hi.
+// The dropped lo.lo term and the tf32 rounding of lo are ~2^-21 relative.
+//
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+//   warp 0      TMA producer: A [128 x 32] and W [bn x 32] fp32 tiles, 128-byte swizzle, 2 stages
+//   warps 8-11  split the landed tiles into hi (in place) / lo (second buffer) in shared memory
+//   warp 1      one elected lane issues the tcgen05.mma triple per K step; tcgen05.commit frees stages
+//   warps 4-7   epilogue: tcgen05.ld the accumulator (double-buffered in TMEM), bias / tanh /
+//               tanh-gradient / row-select, 128-byte row segments straight to global memory
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int BM = 128;                 // rows per tile (UMMA M)
+constexpr int BK = 32;                  // fp32 per K block = one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int MAX_BN = 256;             // UMMA N limit
+constexpr int A_BYTES = BM * BK * 4;    // 16 KB
+constexpr int B_BYTES = MAX_BN * BK * 4;  // 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands = 96 KB
+constexpr int GEMM_THREADS = 384;
+constexpr int SMEM_MISC = 4096;         // barriers, tmem pointer, bias
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 + SMEM_MISC;
+
+enum Epilogue { EPI_BIAS = 0, EPI_BIAS_TANH = 1, EPI_TANH_GRAD = 2, EPI_BIAS_SELECT = 3 };
+
+struct LinearParams {
+  int64_t m;
+  int n, k;          // output columns, reduction length
+  int bn, n_tiles;   // columns per tile, tiles along n
+  const float* bias; // [n] or null
+  float* out0; int ld0; int split;   // columns [0, split) -> out0
+  float* out1; int ld1;              // columns [split, n) -> out1 (may be null when split == n)
+  int epilogue;
+  const float* aux; int ld_aux;      // EPI_TANH_GRAD: tanh output t (y = acc * (1 - t^2)); EPI_BIAS_SELECT: fallback rows
+  const int64_t* rowptr;             // EPI_BIAS_SELECT: row keeps acc + bias iff rowptr[r+1] > rowptr[r]
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major operand tile, 128-byte swizzle, rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
+  return uint64_t((addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128
+__device__ __forceinline__ uint32_t instr_desc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+}
+
+struct Pipe {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                     const LinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* misc = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);       // full[2], ready[2], empty[2], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
+  float* bias_s = reinterpret_cast<float*>(misc + 256);     // up to 768 floats
+  const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + 2), empty_bar = smem_u32(bars + 4);
+  const uint32_t tfull_bar = smem_u32(bars + 6), tempty_bar = smem_u32(bars + 8);
+  const int warp = warp_id(), lane = lane_id();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(ready_bar + 8 * s, 128);
+      mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.n; i += GEMM_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t m_tiles = (p.m + BM - 1) / BM;
+  const int64_t tiles = m_tiles * p.n_tiles;
+  const int k_blocks = p.k / BK;
+  const uint32_t b_tile_bytes = uint32_t(p.bn) * BK * 4;
+
+  if (warp == 0) {
+    // ---------------- TMA producer
+    if (lane == 0) {
+      Pipe pipe;
+      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = int((t / p.n_tiles) * BM), n0 = int(t % p.n_tiles) * p.bn;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar + 8 * pipe.stage, pipe.phase ^ 1);
+          uint8_t* st = smem + pipe.stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar + 8 * pipe.stage, A_BYTES + b_tile_bytes);
+          tma_load_2d(smem_u32(st), &map_a, kb * BK, m0, full_bar + 8 * pipe.stage);
+          tma_load_2d(smem_u32(st + 2 * A_BYTES), &map_w, kb * BK, n0, full_bar + 8 * pipe.stage);
+          pipe.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    Pipe pipe;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t idesc = instr_desc_tf32(p.bn);
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * MAX_BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(ready_bar + 8 * pipe.stage, pipe.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(smem + pipe.stage * STAGE_BYTES);
+          const uint64_t a_hi = smem_desc_k_sw128(st), a_lo = smem_desc_k_sw128(st + A_BYTES);
+          const uint64_t b_hi = smem_desc_k_sw128(st + 2 * A_BYTES), b_lo = smem_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint64_t adv = uint64_t(kk * 32 >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle row
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | kk) != 0);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(empty_bar + 8 * pipe.stage);
+          if (kb == k_blocks - 1) umma_commit(tfull_bar + 8 * acc);
+        }
+        __syncwarp();
+        pipe.advance();
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ---------------- operand split: hi = rn_tf32(x) in place, lo = x - hi
+    Pipe pipe;
+    const int tid = threadIdx.x - 256;
+    const int a_vec = A_BYTES / 16, b_vec = int(b_tile_bytes / 16);
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar + 8 * pipe.stage, pipe.phase);
+        uint8_t* st = smem + pipe.stage * STAGE_BYTES;
+        for (int i = tid; i < a_vec + b_vec; i += 128) {
+          uint8_t* hi_p = i < a_vec ? st + i * 16 : st + 2 * A_BYTES + (i - a_vec) * 16;
+          uint8_t* lo_p = hi_p + (i < a_vec ? A_BYTES : B_BYTES);
+          const float4 v = *reinterpret_cast<const float4*>(hi_p);
+          float4 h, l;
+          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+          *reinterpret_cast<float4*>(hi_p) = h;
+          *reinterpret_cast<float4*>(lo_p) = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(ready_bar + 8 * pipe.stage);
+        pipe.advance();
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int quad = warp - 4;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int64_t row = (t / p.n_tiles) * BM + quad * 32 + lane;
+      const int n0 = int(t % p.n_tiles) * p.bn;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      bool keep = true;
+      if (p.epilogue == EPI_BIAS_SELECT && row < p.m) keep = p.rowptr[row + 1] > p.rowptr[row];
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * MAX_BN + c0), r);
+        if (row < p.m) {
+          const int n = n0 + c0;
+          float* dst = n < p.split ? p.out0 + row * p.ld0 + n : p.out1 + row * p.ld1 + (n - p.split);
+          const float* aux = p.aux ? p.aux + row * p.ld_aux + n : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 y = make_float4(__uint_as_float(r[j]) + bias_s[n + j], __uint_as_float(r[j + 1]) + bias_s[n + j + 1],
+                                   __uint_as_float(r[j + 2]) + bias_s[n + j + 2], __uint_as_float(r[j + 3]) + bias_s[n + j + 3]);
+            if (p.epilogue == EPI_BIAS_TANH) {
+              y = make_float4(tanhf(y.x), tanhf(y.y), tanhf(y.z), tanhf(y.w));
+            } else if (p.epilogue == EPI_TANH_GRAD) {
+              const float4 a = *reinterpret_cast<const float4*>(aux + j);
+              y = make_float4(y.x * (1.f - a.x * a.x), y.y * (1.f - a.y * a.y), y.z * (1.f - a.z * a.z), y.w * (1.f - a.w * a.w));
+            } else if (p.epilogue == EPI_BIAS_SELECT) {
+              if (!keep) y = *reinterpret_cast<const float4*>(aux + j);
+            }
+            *reinterpret_cast<float4*>(dst + j) = y;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + 8 * acc);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// row-major fp32 [rows, cols] -> boxes of [box_rows, 32 cols], 128-byte swizzle, zero fill out of bounds
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  PC_REQUIRE(fn, PC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
+  cuuint32_t box[2] = {BK, cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PC_REQUIRE(r == CUDA_SUCCESS, PC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] ld %lld", int(r),
+             (long long)rows, (long long)cols, (long long)ld);
+  return PC_OK;
+}
+
+}  // namespace
+}  // namespace pc
+
+using namespace pc;
+
+extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, const float* bias,
+                                int epilogue, const float* aux, int64_t ld_aux, const int64_t* rowptr, float* out0,
+                                int64_t ld0, int split, float* out1, int64_t ld1, pc_stream_t stream) {
+  PC_REQUIRE(m >= 0, PC_ERR_INVALID, "linear: negative row count");
+  if (m == 0) return PC_OK;
+  PC_REQUIRE(a && w && out0, PC_ERR_INVALID, "linear: null pointer");
+  PC_REQUIRE(k >= BK && k % BK == 0 && k <= 4096, PC_ERR_UNSUPPORTED, "linear: k=%d must be a multiple of %d", k, BK);
+  PC_REQUIRE(n >= 32 && n % 32 == 0 && n <= 768, PC_ERR_UNSUPPORTED, "linear: n=%d must be a multiple of 32 in [32, 768]", n);
+  PC_REQUIRE(split > 0 && split <= n && split % 32 == 0 && (split == n || out1), PC_ERR_INVALID, "linear: bad output split");
+  PC_REQUIRE(lda % 4 == 0 && ld0 % 4 == 0 && (split == n || ld1 % 4 == 0), PC_ERR_INVALID, "linear: leading dimensions must be multiples of 4 floats");
+  PC_REQUIRE(epilogue >= EPI_BIAS && epilogue <= EPI_BIAS_SELECT, PC_ERR_INVALID, "linear: unknown epilogue %d", epilogue);
+  PC_REQUIRE((epilogue != EPI_TANH_GRAD && epilogue != EPI_BIAS_SELECT) || (aux && ld_aux % 4 == 0), PC_ERR_INVALID, "linear: epilogue needs aux");
+  PC_REQUIRE(epilogue != EPI_BIAS_SELECT || rowptr, PC_ERR_INVALID, "linear: select epilogue needs rowptr");
+  LinearParams p;
+  p.m = m; p.n = n; p.k = k;
+  p.n_tiles = (n + MAX_BN - 1) / MAX_BN;
+  while (n % p.n_tiles != 0 || (n / p.n_tiles) % 32 != 0) ++p.n_tiles;
+  p.bn = n / p.n_tiles;
+  p.bias = bias;
+  p.out0 = out0; p.ld0 = int(ld0); p.split = split; p.out1 = out1; p.ld1 = int(ld1);
+  p.epilogue = epilogue; p.aux = aux; p.ld_aux = int(ld_aux); p.rowptr = rowptr;
+  CUtensorMap map_a, map_w;
+  if (int rc = make_map(&map_a, a, m, k, lda, BM)) return rc;
+  if (int rc = make_map(&map_w, w, n, k, k, p.bn)) return rc;
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    configured = true;
+  }
+  const int64_t tiles = ((m + BM - 1) / BM) * p.n_tiles;
+  const int grid = int(tiles < sm_count() ? tiles : sm_count());
+  linear_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, as_stream(stream)>>>(map_a, map_w, p);
+  PC_LAUNCH_CHECK();
+  return PC_OK;
+}

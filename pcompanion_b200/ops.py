@@ -198,6 +198,29 @@ def gat_attention(q: torch.Tensor, kv: torch.Tensor, graph: CSRGraph, heads: int
     return _GATAttention.apply(q, kv, graph, heads, dropout_p, seed)
 
 
+# --------------------------------------------------------------------------- dense projections (tcgen05)
+EPI_BIAS, EPI_BIAS_TANH, EPI_TANH_GRAD, EPI_BIAS_SELECT = 0, 1, 2, 3
+
+
+def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
+              aux: Optional[torch.Tensor] = None, rowptr: Optional[torch.Tensor] = None, split: Optional[int] = None):
+    """epilogue(A . W^T + bias) on the tensor cores (pc_linear_tf32x3).  Returns one [m, n] tensor, or
+    ([m, split], [m, n - split]) when `split` is given."""
+    m, k = a.shape
+    n = w.shape[0]
+    if a.stride(1) != 1 or w.stride() != (k, 1):
+        raise ValueError("linear_tc: A must have unit column stride and W must be contiguous [n, k]")
+    split_ = n if split is None else split
+    out0 = torch.empty(m, split_, dtype=F32, device=a.device)
+    out1 = torch.empty(m, n - split_, dtype=F32, device=a.device) if split_ < n else None
+    if not a.is_cuda or a.dtype != F32:
+        raise RuntimeError(f"linear_tc: A must be a float32 CUDA tensor (got {a.dtype} on {a.device}); no CPU fallback")
+    call("pc_linear_tf32x3", _lib.c_void_p(a.data_ptr()), m, k, a.stride(0), dev(w, F32, "w"), n, dev(bias, F32, "bias"), epilogue, dev(aux, F32, "aux"),
+         aux.stride(0) if aux is not None else 0, dev(rowptr, I64, "rowptr"), dev(out0, F32, "out0"), split_, split_,
+         dev(out1, F32, "out1"), (n - split_), stream())
+    return out0 if out1 is None else (out0, out1)
+
+
 # --------------------------------------------------------------------------- hinge losses
 class _HingeRows(torch.autograd.Function):
     @staticmethod

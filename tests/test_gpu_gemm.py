@@ -1,0 +1,76 @@
+"""tcgen05 3xTF32 projection kernel vs a float64 reference (1e-5 relative, BASELINE.json's fp32 gate)."""
+import numpy as np
+import pytest
+import torch
+
+from test_gpu_parity import close, dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("m,k,n", [(1000, 128, 256), (128, 256, 256), (37, 256, 128), (4096 + 5, 128, 128), (513, 384, 128),
+                                   (300, 64, 32), (300, 32, 64)])
+def test_linear_bias_matches_float64(m, k, n):
+    from pcompanion_b200 import ops
+    g = torch.Generator(device=dev()).manual_seed(m + k + n)
+    a = torch.randn(m, k, generator=g, device=dev())
+    w = torch.randn(n, k, generator=g, device=dev()) * 0.1
+    b = torch.randn(n, generator=g, device=dev())
+    y = ops.linear_tc(a, w, b)
+    ref = a.double() @ w.double().T + b.double()
+    close(y, ref.cpu().numpy(), what=f"linear {m}x{k}x{n}")
+    y2 = ops.linear_tc(a, w, None)
+    close(y2, (a.double() @ w.double().T).cpu().numpy(), what="no bias")
+    assert torch.equal(ops.linear_tc(a, w, b), y)                      # deterministic
+
+
+def test_linear_epilogues_and_split_outputs():
+    from pcompanion_b200 import ops
+    g = torch.Generator(device=dev()).manual_seed(0)
+    m = 777
+    a = torch.randn(m, 128, generator=g, device=dev())
+    w = torch.randn(384, 128, generator=g, device=dev()) * 0.1
+    b = torch.randn(384, generator=g, device=dev())
+    ref = (a.double() @ w.double().T + b.double()).cpu().numpy()
+    q, kv = ops.linear_tc(a, w, b, split=128)                         # packed in-projection: Q | K|V
+    assert q.shape == (m, 128) and kv.shape == (m, 256)
+    close(q, ref[:, :128], what="q"); close(kv, ref[:, 128:], what="kv")
+    w2 = torch.randn(256, 128, generator=g, device=dev()) * 0.1
+    b2 = torch.randn(256, generator=g, device=dev())
+    t = ops.linear_tc(a, w2, b2, ops.EPI_BIAS_TANH)
+    ref_t = np.tanh((a.double() @ w2.double().T + b2.double()).cpu().numpy())
+    close(t, ref_t, what="tanh")
+    # gradient through tanh: (dY . W) * (1 - t^2) with the transposed weight as the kernel's W
+    dy = torch.randn(m, 128, generator=g, device=dev())
+    wt = w2.t().contiguous()                                         # [128, 256]: dX = dY[m,256] . W[256,128] -> here dY is [m,128]
+    dpre = ops.linear_tc(dy, wt.t().contiguous(), None, ops.EPI_TANH_GRAD, aux=t)   # W' = [256,128]: y = dy . W'^T -> [m,256]
+    ref_d = (dy.double() @ wt.double()).cpu().numpy() * (1 - ref_t ** 2)
+    close(dpre, ref_d, what="tanh grad")
+    # row select (product2vec.py:76: rows without neighbours keep ffn(x))
+    rowptr = torch.cumsum(torch.tensor([0] + [i % 3 for i in range(m)], device=dev()), 0)
+    h = torch.randn(m, 128, generator=g, device=dev())
+    w3 = torch.randn(128, 128, generator=g, device=dev()) * 0.1
+    b3 = torch.randn(128, generator=g, device=dev())
+    out = ops.linear_tc(a, w3, b3, ops.EPI_BIAS_SELECT, aux=h, rowptr=rowptr)
+    ref_o = (a.double() @ w3.double().T + b3.double()).cpu().numpy()
+    keep = (np.arange(m) % 3 != 0)[:, None]
+    close(out, np.where(keep, ref_o, h.cpu().numpy()), what="select")
+    # strided A (a column slice of a wider tensor)
+    wide = torch.randn(m, 384, generator=g, device=dev())
+    ys = ops.linear_tc(wide[:, 128:256], w3, b3)
+    close(ys, (wide[:, 128:256].double() @ w3.double().T + b3.double()).cpu().numpy(), what="strided A")
+
+
+def test_linear_large_m_matches_cublas_fp32():
+    from pcompanion_b200 import ops
+    g = torch.Generator(device=dev()).manual_seed(1)
+    m = 200_003
+    a = torch.randn(m, 256, generator=g, device=dev())
+    w = torch.randn(256, 256, generator=g, device=dev()) * 0.06
+    b = torch.randn(256, generator=g, device=dev())
+    y = ops.linear_tc(a, w, b)
+    ref = torch.nn.functional.linear(a, w, b)
+    rel = ((y - ref).norm() / ref.norm()).item()
+    assert rel < 2e-6, rel
+    sub = slice(0, m, 997)
+    close(y[sub], (a[sub].double() @ w.double().T + b.double()).cpu().numpy(), what="large m sample")
