@@ -299,6 +299,203 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   }
 }
 
+// ================================================================ weight gradient
+// dW[n, k] = sum_m dY[m, n] * X[m, k]  (+ db[n] = sum_m dY[m, n]): the reduction runs over the
+// rows of two row-major activations, so both MMA operands are MN-major: a stage holds 16 rows
+// of dY and X as [32-column group][16 rows][128 bytes] blocks (128-byte swizzle), which is the
+// canonical MN-major layout for 32-bit operands (32-byte-atom swizzle) with LBO = 2048 (next 32
+// columns) and SBO = 512 (next 4 rows).
+// Every CTA reduces a strided subset of 16-row blocks into TMEM, dumps one partial [n, k] to a
+// workspace, and a second kernel sums the partials in CTA order (deterministic, no atomics).
+constexpr int WG_ROWS = 16;                        // reduction rows per stage (2 x UMMA_K)
+constexpr int WG_STAGES = 3;
+constexpr int WG_MAX_COLS = 256;
+constexpr int WG_OP_BYTES = WG_MAX_COLS * WG_ROWS * 4;   // 16 KB per operand per stage
+constexpr int WG_STAGE_BYTES = 4 * WG_OP_BYTES;          // dY hi/lo + X hi/lo
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + SMEM_MISC;
+constexpr int WG_GROUP_BYTES = WG_ROWS * 128;            // one 32-column group of a stage
+
+struct WgradParams {
+  int64_t m;
+  int n, k;            // dY columns (rows of dW), X columns (cols of dW)
+  float* partial_w;    // [grid, n, k]
+  float* partial_b;    // [grid, n] or null
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+// MN-major 32-bit operand: the only legal layout is SWIZZLE_128B_BASE32B (32-byte chunks of a 128-byte row
+// XOR-ed with the row index mod 4; atom = 128 bytes of MN x 4 K rows).  LBO = stride between 32-element MN
+// groups, SBO = stride between 4-row K groups (an 8-deep tf32 MMA spans two of them).
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr) {
+  return uint64_t((addr & 0x3FFFFu) >> 4) | (uint64_t(WG_GROUP_BYTES >> 4) << 16) | (uint64_t(512 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
+__device__ __forceinline__ uint32_t instr_desc_tf32_mn(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+}
+
+struct WgPipe {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == WG_STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                    const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* misc = smem + WG_STAGES * WG_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // full[3], ready[3], empty[3], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
+  float* bias_s = reinterpret_cast<float*>(misc + 256); // [2][n] column sums from the two thread halves
+  const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + 3), empty_bar = smem_u32(bars + 6);
+  const uint32_t done_bar = smem_u32(bars + 9);
+  const int warp = warp_id(), lane = lane_id();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(ready_bar + 8 * s, 128);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t blocks = (p.m + WG_ROWS - 1) / WG_ROWS;
+  const uint32_t dy_bytes = uint32_t(p.n) * WG_ROWS * 4, x_bytes = uint32_t(p.k) * WG_ROWS * 4;
+  const int halves = p.n / BM;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      WgPipe pipe;
+      for (int64_t b = blockIdx.x; b < blocks; b += gridDim.x) {
+        mbar_wait(empty_bar + 8 * pipe.stage, pipe.phase ^ 1);
+        uint8_t* st = smem + pipe.stage * WG_STAGE_BYTES;
+        mbar_arrive_expect_tx(full_bar + 8 * pipe.stage, dy_bytes + x_bytes);
+        tma_load_3d(smem_u32(st), &map_dy, 0, int(b * WG_ROWS), 0, full_bar + 8 * pipe.stage);
+        tma_load_3d(smem_u32(st + 2 * WG_OP_BYTES), &map_x, 0, int(b * WG_ROWS), 0, full_bar + 8 * pipe.stage);
+        pipe.advance();
+      }
+    }
+  } else if (warp == 1) {
+    WgPipe pipe;
+    const uint32_t idesc = instr_desc_tf32_mn(p.k);
+    bool first = true;
+    for (int64_t b = blockIdx.x; b < blocks; b += gridDim.x) {
+      mbar_wait(ready_bar + 8 * pipe.stage, pipe.phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + pipe.stage * WG_STAGE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
+          const uint64_t b_hi = smem_desc_mn_sw128(st + 2 * WG_OP_BYTES + ks * 1024);
+          const uint64_t b_lo = smem_desc_mn_sw128(st + 3 * WG_OP_BYTES + ks * 1024);
+          for (int h = 0; h < halves; ++h) {
+            const uint32_t a_off = uint32_t(h * 4 * WG_GROUP_BYTES + ks * 1024);
+            const uint64_t a_hi = smem_desc_mn_sw128(st + a_off), a_lo = smem_desc_mn_sw128(st + WG_OP_BYTES + a_off);
+            const uint32_t d = tmem_base + uint32_t(h * WG_MAX_COLS);
+            umma_tf32(d, a_lo, b_hi, idesc, (first && ks == 0) ? 0u : 1u);
+            umma_tf32(d, a_hi, b_lo, idesc, 1);
+            umma_tf32(d, a_hi, b_hi, idesc, 1);
+          }
+        }
+        umma_commit(empty_bar + 8 * pipe.stage);
+      }
+      __syncwarp();
+      first = false;
+      pipe.advance();
+    }
+    if (lane == 0) umma_commit(done_bar);
+    __syncwarp();
+  } else if (warp >= 8) {
+    // split hi/lo; threads own a fixed (group, 16-byte chunk) pair so that dY column sums stay in registers
+    WgPipe pipe;
+    const int tid = threadIdx.x - 256;
+    const int dy_pairs = p.n / 4, x_pairs = p.k / 4;
+    float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t b = blockIdx.x; b < blocks; b += gridDim.x) {
+      mbar_wait(full_bar + 8 * pipe.stage, pipe.phase);
+      uint8_t* st = smem + pipe.stage * WG_STAGE_BYTES;
+      for (int pr = tid; pr < dy_pairs + x_pairs; pr += 128) {
+        const bool is_dy = pr < dy_pairs;
+        const int q = is_dy ? pr : pr - dy_pairs;
+        uint8_t* base = st + (is_dy ? 0 : 2 * WG_OP_BYTES) + (q >> 3) * WG_GROUP_BYTES;
+        const int c = q & 7;
+#pragma unroll 4
+        for (int r = 0; r < WG_ROWS; ++r) {
+          uint8_t* hi_p = base + r * 128 + (((((c >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4);
+          const float4 v = *reinterpret_cast<const float4*>(hi_p);
+          float4 h, l;
+          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+          *reinterpret_cast<float4*>(hi_p) = h;
+          *reinterpret_cast<float4*>(hi_p + WG_OP_BYTES) = l;
+          if (is_dy && pr == tid) { colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w; }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(ready_bar + 8 * pipe.stage);
+      pipe.advance();
+    }
+    if (p.partial_b && tid < dy_pairs) {
+      // logical chunk c of group g covers columns g*32 + 4c .. +3 (the swizzle only permutes positions)
+      *reinterpret_cast<float4*>(p.partial_b + int64_t(blockIdx.x) * p.n + (tid >> 3) * 32 + (tid & 7) * 4) = colsum;
+    }
+  } else if (warp >= 4) {
+    const int quad = warp - 4;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* out = p.partial_w + int64_t(blockIdx.x) * p.n * p.k;
+    for (int h = 0; h < halves; ++h) {
+      const int row = h * BM + quad * 32 + lane;
+      for (int c0 = 0; c0 < p.k; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(h * WG_MAX_COLS + c0), r);
+        float* dst = out + int64_t(row) * p.k + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+    }
+    tc_fence_before();
+  }
+  (void)bias_s;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// out[i] = sum_c partial[c, i] in ascending c (fixed order)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int parts, int64_t n, float* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int c = 0; c < parts; ++c) acc += partial[int64_t(c) * n + i];
+  out[i] = acc;
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -370,5 +567,59 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   const int grid = int(tiles < sm_count() ? tiles : sm_count());
   linear_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, as_stream(stream)>>>(map_a, map_w, p);
   PC_LAUNCH_CHECK();
+  return PC_OK;
+}
+
+// row-major fp32 [rows, cols] viewed as [cols/32 groups][rows][32]: boxes of [groups, 16 rows, 32 cols]
+static int make_map_mn(CUtensorMap* map, const float* base, int64_t rows, int cols, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled();
+  PC_REQUIRE(fn, PC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[3] = {32, cuuint64_t(rows), cuuint64_t(cols / 32)};
+  cuuint64_t gstride[2] = {cuuint64_t(ld) * 4, 128};
+  cuuint32_t box[3] = {32, WG_ROWS, cuuint32_t(cols / 32)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PC_REQUIRE(r == CUDA_SUCCESS, PC_ERR_CUDA, "cuTensorMapEncodeTiled (3d) failed (%d)", int(r));
+  return PC_OK;
+}
+
+extern "C" size_t pc_wgrad_workspace_bytes(int n, int k) {
+  return size_t(sm_count()) * (size_t(n) * k + size_t(n)) * sizeof(float);
+}
+
+extern "C" int pc_wgrad_tf32x3(const float* dy, int64_t m, int n, int64_t ld_dy, const float* x, int k, int64_t ld_x,
+                               float* dw, float* db, void* workspace, size_t workspace_bytes, pc_stream_t stream) {
+  PC_REQUIRE(m > 0, PC_ERR_INVALID, "wgrad: need at least one row");
+  PC_REQUIRE(dy && x && dw && workspace, PC_ERR_INVALID, "wgrad: null pointer");
+  PC_REQUIRE((n == 128 || n == 256) && k >= 32 && k % 32 == 0 && k <= WG_MAX_COLS, PC_ERR_UNSUPPORTED,
+             "wgrad: n=%d must be 128 or 256 and k=%d a multiple of 32 up to 256", n, k);
+  PC_REQUIRE(ld_dy % 4 == 0 && ld_x % 4 == 0, PC_ERR_INVALID, "wgrad: leading dimensions must be multiples of 4 floats");
+  PC_REQUIRE(workspace_bytes >= pc_wgrad_workspace_bytes(n, k), PC_ERR_WORKSPACE, "wgrad: workspace too small");
+  const int64_t blocks = (m + WG_ROWS - 1) / WG_ROWS;
+  const int grid = int(blocks < sm_count() ? blocks : sm_count());
+  WgradParams p;
+  p.m = m; p.n = n; p.k = k;
+  p.partial_w = reinterpret_cast<float*>(workspace);
+  p.partial_b = db ? p.partial_w + size_t(grid) * n * k : nullptr;
+  CUtensorMap map_dy, map_x;
+  if (int rc = make_map_mn(&map_dy, dy, m, n, ld_dy)) return rc;
+  if (int rc = make_map_mn(&map_x, x, m, k, ld_x)) return rc;
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA(cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    configured = true;
+  }
+  cudaStream_t st = as_stream(stream);
+  wgrad_tf32x3_kernel<<<grid, GEMM_THREADS, WG_SMEM, st>>>(map_dy, map_x, p);
+  PC_LAUNCH_CHECK();
+  const int64_t nk = int64_t(n) * k;
+  reduce_partials_kernel<<<unsigned((nk + 255) / 256), 256, 0, st>>>(p.partial_w, grid, nk, dw);
+  PC_LAUNCH_CHECK();
+  if (db) {
+    reduce_partials_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(p.partial_b, grid, n, db);
+    PC_LAUNCH_CHECK();
+  }
   return PC_OK;
 }

@@ -1,22 +1,72 @@
-"""Dense per-row projections of the hot path (FFN chain, Q / K|V / out projections, the small
-type-transition and item-prediction layers).
+"""Dense per-row projections of the hot path (FFN chain, Q / K|V / out projections).
 
-These are the only GEMM-shaped operations on the path.  They are
-plain library GEMMs: torch dispatches them to cuBLAS in full fp32 (TF32 is left disabled so the
-1e-5 parity gate of BASELINE.json holds), with BatchNorm / tanh as ATen elementwise kernels.
-Everything irregular - gathers, segmented softmax, scatter, hinge reductions, sort / set logic,
-top-K - is hand-written CUDA behind the C ABI.  CUDA tensors only: there is no CPU path.
+The Product2Vec projections (128/256/384-wide) run on the tensor cores
+through pcompanion_b200/csrc/gemm.cu: tcgen05.mma kind::tf32 with a 3-way hi/lo operand split
+(fp32-faithful, so the 1e-5 parity gate holds), TMA-fed, accumulators in TMEM; forward, input
+gradient (same kernel on the transposed weight) and weight / bias gradient (MN-major operands,
+deterministic split reduction).  Layers whose shape the kernels are not instantiated for (the
+64 -> 32 -> 64 type-transition MLP and the 64 -> 128 type projection of P-Companion, a few
+hundred rows per step) are plain library GEMMs (cuBLAS via torch, full fp32).  BatchNorm
+statistics / normalisation and tanh are elementwise passes.  CUDA tensors only.
 """
 from __future__ import annotations
+
+from typing import Optional
 
 import torch
 import torch.nn.functional as F
 
+from . import ops
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
+
+def _tc_shape_ok(k: int, n: int) -> bool:
+    return k in (128, 256) and n in (128, 256)
+
+
+class _LinearTC(torch.autograd.Function):
+    """y = act(x W^T + b) with act in {identity, tanh}; all three GEMMs on tcgen05."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, tanh: bool):
+        x = x if x.stride(-1) == 1 else x.contiguous()
+        y = ops.linear_tc(x, weight.contiguous(), bias, ops.EPI_BIAS_TANH if tanh else ops.EPI_BIAS)
+        ctx.save_for_backward(x, weight, y if tanh else None)
+        ctx.tanh = tanh
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.tanh:
+            dy = dy * (1.0 - y * y)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear_tc(dy, weight.t().contiguous(), None)          # dX = dY . W
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.wgrad_tc(dy, x, want_bias=ctx.has_bias)
+        return dx, dw, db, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], tanh: bool = False) -> torch.Tensor:
+    """nn.Linear (optionally followed by tanh) on [rows, k] -> [rows, n]."""
     if not x.is_cuda:
         raise RuntimeError(f"pcompanion_b200.dense.linear: input on {x.device}; CUDA only (no CPU fallback)")
-    return F.linear(x, weight, bias)
+    n, k = weight.shape
+    if x.dim() == 2 and _tc_shape_ok(k, n) and x.dtype == torch.float32:
+        return _LinearTC.apply(x, weight, bias, tanh)
+    y = F.linear(x, weight, bias)
+    return torch.tanh(y) if tanh else y
+
+
+def in_projection(h_query: torch.Tensor, h_kv: torch.Tensor, w: torch.Tensor, b: torch.Tensor):
+    """Packed in-projection of nn.MultiheadAttention for query != key, key is value
+    (torch F._in_projection_packed): Q from rows [0:E] of in_proj_weight, K|V from rows [E:3E]."""
+    e = w.shape[1]
+    q = linear(h_query, w[:e], b[:e])
+    kv = linear(h_kv, w[e:], b[e:])
+    return q, kv
 
 
 def ffn_forward(ffn: torch.nn.Sequential, rows: torch.Tensor, training: bool) -> torch.Tensor:
@@ -31,5 +81,5 @@ def ffn_forward(ffn: torch.nn.Sequential, rows: torch.Tensor, training: bool) ->
         bn.num_batches_tracked.add_(1)
     z = F.batch_norm(z, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum, bn.eps)
     z = torch.tanh(z)
-    z = torch.tanh(linear(z, l3.weight, l3.bias))
+    z = linear(z, l3.weight, l3.bias, tanh=True)
     return linear(z, l5.weight, l5.bias)

@@ -221,6 +221,22 @@ def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
     return out0 if out1 is None else (out0, out1)
 
 
+def wgrad_tc(dy: torch.Tensor, x: torch.Tensor, want_bias: bool = True):
+    """(dW [n, k], db [n] | None) = (dY^T X, column sums of dY) on the tensor cores (pc_wgrad_tf32x3)."""
+    m, n = dy.shape
+    k = x.shape[1]
+    if dy.stride(1) != 1 or x.stride(1) != 1 or x.shape[0] != m:
+        raise ValueError("wgrad_tc: dY [m, n] and X [m, k] must have unit column stride and equal row counts")
+    if not (dy.is_cuda and x.is_cuda and dy.dtype == F32 and x.dtype == F32):
+        raise RuntimeError("wgrad_tc: float32 CUDA tensors required; no CPU fallback")
+    dw = torch.empty(n, k, dtype=F32, device=dy.device)
+    db = torch.empty(n, dtype=F32, device=dy.device) if want_bias else None
+    ws = _lib.workspace(_lib.LIB.pc_wgrad_workspace_bytes(n, k), dy.device)
+    call("pc_wgrad_tf32x3", _lib.c_void_p(dy.data_ptr()), m, n, dy.stride(0), _lib.c_void_p(x.data_ptr()), k, x.stride(0),
+         dev(dw, F32, "dw"), dev(db, F32, "db"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return dw, db
+
+
 # --------------------------------------------------------------------------- hinge losses
 class _HingeRows(torch.autograd.Function):
     @staticmethod

@@ -74,3 +74,48 @@ def test_linear_large_m_matches_cublas_fp32():
     assert rel < 2e-6, rel
     sub = slice(0, m, 997)
     close(y[sub], (a[sub].double() @ w.double().T + b.double()).cpu().numpy(), what="large m sample")
+
+
+@pytest.mark.parametrize("m,n,k", [(1000, 256, 256), (16, 128, 128), (5, 128, 256), (33_333, 256, 128), (4097, 128, 32)])
+def test_wgrad_matches_float64_and_is_deterministic(m, n, k):
+    from pcompanion_b200 import ops
+    g = torch.Generator(device=dev()).manual_seed(m + n + k)
+    dy = torch.randn(m, n, generator=g, device=dev())
+    x = torch.randn(m, k, generator=g, device=dev())
+    dw, db = ops.wgrad_tc(dy, x)
+    close(dw, (dy.double().T @ x.double()).cpu().numpy(), what=f"dW {m}x{n}x{k}")
+    close(db, dy.double().sum(0).cpu().numpy(), what="db")
+    dw2, db2 = ops.wgrad_tc(dy, x)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    dw3, none = ops.wgrad_tc(dy, x, want_bias=False)
+    assert none is None and torch.equal(dw3, dw)
+
+
+def test_wgrad_strided_operands():
+    from pcompanion_b200 import ops
+    g = torch.Generator(device=dev()).manual_seed(9)
+    wide = torch.randn(3000, 384, generator=g, device=dev())
+    x = torch.randn(3000, 128, generator=g, device=dev())
+    dy = wide[:, 128:]                                                # [m, 256] view with row stride 384
+    dw, db = ops.wgrad_tc(dy, x)
+    close(dw, (dy.double().T @ x.double()).cpu().numpy(), what="dW strided")
+    close(db, dy.double().sum(0).cpu().numpy(), what="db strided")
+
+
+def test_linear_autograd_function_matches_torch_autograd():
+    from pcompanion_b200 import dense
+    g = torch.Generator(device=dev()).manual_seed(3)
+    x = torch.randn(513, 128, generator=g, device=dev(), requires_grad=True)
+    w = (torch.randn(256, 128, generator=g, device=dev()) * 0.1).requires_grad_(True)
+    b = torch.randn(256, generator=g, device=dev(), requires_grad=True)
+    up = torch.randn(513, 256, generator=g, device=dev())
+    for tanh in (False, True):
+        for t in (x, w, b):
+            t.grad = None
+        (dense.linear(x, w, b, tanh=tanh) * up).sum().backward()
+        got = [t.grad.clone() for t in (x, w, b)]
+        x64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        y = torch.nn.functional.linear(x64, w64, b64)
+        ((torch.tanh(y) if tanh else y) * up.double()).sum().backward()
+        for a, r, nm in zip(got, (x64, w64, b64), ("dx", "dw", "db")):
+            close(a, r.grad.cpu().numpy(), what=f"{nm} tanh={tanh}")
