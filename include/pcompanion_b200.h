@@ -120,7 +120,7 @@ int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float*
 
 /* Weight / bias gradient of such a projection (autograd's AddmmBackward for the weight):
  *   dW[n, k] = sum_m dY[m, n] X[m, k],  db[n] = sum_m dY[m, n]  (db may be NULL)
- * n in {128, 256}, k % 32 == 0, k <= 256; fixed reduction order (bit-reproducible). */
+ * n % 128 == 0, k % 32 == 0, k <= 256; fixed reduction order (bit-reproducible). */
 size_t pc_wgrad_workspace_bytes(int n, int k);
 int pc_wgrad_tf32x3(const float* dy, int64_t m, int n, int64_t ld_dy, const float* x, int k, int64_t ld_x, float* dw,
                     float* db, void* workspace, size_t workspace_bytes, pc_stream_t stream);

@@ -8,13 +8,17 @@
 // parity, which single-pass TF32/BF16 tensor-core math (~1e-3) cannot give.  Each operand is
 // therefore split on the fly into hi = rn_tf32(x) and lo = x - hi, and three tcgen05.mma
 // (kind::tf32, fp32 accumulation in TMEM) are issued per K step: lo.hi + hi.lo + hi.hi.
-// The dropped lo.lo term and the tf32 rounding of lo are ~2^-21 relative.
+// The dropped lo.lo term and the tf32 rounding of lo are ~2^-21 relative.  The tensor core
+// accumulates with truncation (measured: -2.4e-8 relative per MMA on same-sign data,
+// profiles/gemm_accuracy.py), so the hi.hi chain and the small cross terms go to two separate
+// TMEM accumulators (the cross terms would otherwise cost a truncation at the full magnitude
+// each) and are added once, rounded, in the epilogue.
 //
-// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
-//   warp 0      TMA producer: A [128 x 32] and W [bn x 32] fp32 tiles, 128-byte swizzle, 2 stages
-//   warps 8-11  split the landed tiles into hi (in place) / lo (second buffer) in shared memory
+// Structure (one persistent CTA per SM, 512 threads, warp-specialised):
+//   warp 0      TMA producer: A [128 x 32] and W [bn x 32] fp32 tiles, 128-byte swizzle, 3 stages
+//   warps 8-15  split the landed tiles into hi (in place) / lo (second buffer) in shared memory
 //   warp 1      one elected lane issues the tcgen05.mma triple per K step; tcgen05.commit frees stages
-//   warps 4-7   epilogue: tcgen05.ld the accumulator (double-buffered in TMEM), bias / tanh /
+//   warps 4-7   epilogue: tcgen05.ld both accumulators (double-buffered in TMEM), bias / tanh /
 //               tanh-gradient / row-select, 128-byte row segments straight to global memory
 #include <cuda.h>
 #include <math.h>
@@ -26,12 +30,13 @@ namespace {
 
 constexpr int BM = 128;                 // rows per tile (UMMA M)
 constexpr int BK = 32;                  // fp32 per K block = one 128-byte swizzle row
-constexpr int STAGES = 2;
-constexpr int MAX_BN = 256;             // UMMA N limit
+constexpr int STAGES = 3;
+constexpr int MAX_BN = 128;             // columns per tile: 2 accumulators x 2 buffers x 128 = the 512 TMEM columns
 constexpr int A_BYTES = BM * BK * 4;    // 16 KB
-constexpr int B_BYTES = MAX_BN * BK * 4;  // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands = 96 KB
-constexpr int GEMM_THREADS = 384;
+constexpr int B_BYTES = MAX_BN * BK * 4;  // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands = 64 KB
+constexpr int GEMM_THREADS = 512;
+constexpr int SPLIT_THREADS = 256;      // warps 8-15
 constexpr int SMEM_MISC = 4096;         // barriers, tmem pointer, bias
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 + SMEM_MISC;
 
@@ -141,18 +146,20 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* misc = smem + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);       // full[2], ready[2], empty[2], tmem_full[2], tmem_empty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);       // full[3], ready[3], empty[3], tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
   float* bias_s = reinterpret_cast<float*>(misc + 256);     // up to 768 floats
-  const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + 2), empty_bar = smem_u32(bars + 4);
-  const uint32_t tfull_bar = smem_u32(bars + 6), tempty_bar = smem_u32(bars + 8);
+  const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + 3), empty_bar = smem_u32(bars + 6);
+  const uint32_t tfull_bar = smem_u32(bars + 9), tempty_bar = smem_u32(bars + 11);
   const int warp = warp_id(), lane = lane_id();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(ready_bar + 8 * s, 128);
+      mbar_init(ready_bar + 8 * s, SPLIT_THREADS);
       mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
       mbar_init(tempty_bar + 8 * s, 128);
     }
@@ -198,7 +205,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + uint32_t(acc * MAX_BN);
+      const uint32_t d_main = tmem_base + uint32_t(acc * 2 * MAX_BN), d_cross = d_main + MAX_BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(ready_bar + 8 * pipe.stage, pipe.phase);
         tc_fence_after();
@@ -209,9 +216,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t adv = uint64_t(kk * 32 >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle row
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | kk) != 0);
-            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | kk) != 0);
+            umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
           }
           umma_commit(empty_bar + 8 * pipe.stage);
           if (kb == k_blocks - 1) umma_commit(tfull_bar + 8 * acc);
@@ -233,7 +240,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(full_bar + 8 * pipe.stage, pipe.phase);
         uint8_t* st = smem + pipe.stage * STAGE_BYTES;
-        for (int i = tid; i < a_vec + b_vec; i += 128) {
+#pragma unroll 4
+        for (int i = tid; i < a_vec + b_vec; i += SPLIT_THREADS) {
           uint8_t* hi_p = i < a_vec ? st + i * 16 : st + 2 * A_BYTES + (i - a_vec) * 16;
           uint8_t* lo_p = hi_p + (i < a_vec ? A_BYTES : B_BYTES);
           const float4 v = *reinterpret_cast<const float4*>(hi_p);
@@ -261,8 +269,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       bool keep = true;
       if (p.epilogue == EPI_BIAS_SELECT && row < p.m) keep = p.rowptr[row + 1] > p.rowptr[row];
       for (int c0 = 0; c0 < p.bn; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * MAX_BN + c0), r);
+        uint32_t r[32], rc[32];
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + c0), r);
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + MAX_BN + c0), rc);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
         if (row < p.m) {
           const int n = n0 + c0;
           float* dst = n < p.split ? p.out0 + row * p.ld0 + n : p.out1 + row * p.ld1 + (n - p.split);
@@ -301,25 +312,30 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
 // ================================================================ weight gradient
 // dW[n, k] = sum_m dY[m, n] * X[m, k]  (+ db[n] = sum_m dY[m, n]): the reduction runs over the
-// rows of two row-major activations, so both MMA operands are MN-major: a stage holds 16 rows
-// of dY and X as [32-column group][16 rows][128 bytes] blocks (128-byte swizzle), which is the
-// canonical MN-major layout for 32-bit operands (32-byte-atom swizzle) with LBO = 2048 (next 32
-// columns) and SBO = 512 (next 4 rows).
-// Every CTA reduces a strided subset of 16-row blocks into TMEM, dumps one partial [n, k] to a
-// workspace, and a second kernel sums the partials in CTA order (deterministic, no atomics).
+// rows of two row-major activations, so both MMA operands are MN-major.  A stage holds 16 rows
+// of a 128-column half of dY and of X as [32-column group][16 rows][128 bytes] blocks, which is
+// the canonical MN-major layout for 32-bit operands (SWIZZLE_128B_BASE32B: 32-byte chunks XOR
+// row mod 4) with LBO = 2048 (next 32 columns) and SBO = 512 (next 4 rows).
+// CTA c owns column half (c mod halves) of dY and every (grid/halves)-th 16-row block.  Because
+// the tensor core accumulates with truncation, a chain is cut every 32 blocks: the two TMEM
+// accumulators (hi.hi and cross terms) are added, rounded, into the CTA's fp32 partial in
+// global memory.  A second kernel sums the partials in CTA order (deterministic, no atomics).
 constexpr int WG_ROWS = 16;                        // reduction rows per stage (2 x UMMA_K)
-constexpr int WG_STAGES = 3;
-constexpr int WG_MAX_COLS = 256;
-constexpr int WG_OP_BYTES = WG_MAX_COLS * WG_ROWS * 4;   // 16 KB per operand per stage
-constexpr int WG_STAGE_BYTES = 4 * WG_OP_BYTES;          // dY hi/lo + X hi/lo
+constexpr int WG_STAGES = 4;
+constexpr int WG_MAX_K = 256;
+constexpr int WG_DY_BYTES = BM * WG_ROWS * 4;      // 8 KB: 128 columns x 16 rows
+constexpr int WG_X_BYTES = WG_MAX_K * WG_ROWS * 4; // 16 KB
+constexpr int WG_STAGE_BYTES = 2 * WG_DY_BYTES + 2 * WG_X_BYTES;   // 48 KB
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + SMEM_MISC;
-constexpr int WG_GROUP_BYTES = WG_ROWS * 128;            // one 32-column group of a stage
+constexpr int WG_GROUP_BYTES = WG_ROWS * 128;      // one 32-column group of a stage
+constexpr int WG_FLUSH = 32;                       // blocks per accumulation chain
 
 struct WgradParams {
   int64_t m;
   int n, k;            // dY columns (rows of dW), X columns (cols of dW)
-  float* partial_w;    // [grid, n, k]
-  float* partial_b;    // [grid, n] or null
+  int halves;          // n / 128
+  float* partial_w;    // [grid / halves, n, k]
+  float* partial_b;    // [2 * grid / halves, n] or null
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
@@ -328,9 +344,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
-// MN-major 32-bit operand: the only legal layout is SWIZZLE_128B_BASE32B (32-byte chunks of a 128-byte row
-// XOR-ed with the row index mod 4; atom = 128 bytes of MN x 4 K rows).  LBO = stride between 32-element MN
-// groups, SBO = stride between 4-row K groups (an 8-deep tf32 MMA spans two of them).
+// MN-major 32-bit operand: the only legal layout is SWIZZLE_128B_BASE32B (atom = 128 bytes of MN x 4 K rows).
+// LBO = stride between 32-element MN groups, SBO = stride between 4-row K groups (an 8-deep tf32 MMA spans two).
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr) {
   return uint64_t((addr & 0x3FFFFu) >> 4) | (uint64_t(WG_GROUP_BYTES >> 4) << 16) | (uint64_t(512 >> 4) << 32) |
          (uint64_t(1) << 46) | (uint64_t(1) << 61);
@@ -356,19 +371,19 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* misc = smem + WG_STAGES * WG_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // full[3], ready[3], empty[3], done
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // full[4], ready[4], empty[4], tmem_full, tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-  float* bias_s = reinterpret_cast<float*>(misc + 256); // [2][n] column sums from the two thread halves
-  const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + 3), empty_bar = smem_u32(bars + 6);
-  const uint32_t done_bar = smem_u32(bars + 9);
+  const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + 4), empty_bar = smem_u32(bars + 8);
+  const uint32_t tfull_bar = smem_u32(bars + 12), tempty_bar = smem_u32(bars + 13);
   const int warp = warp_id(), lane = lane_id();
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(ready_bar + 8 * s, 128);
+      mbar_init(ready_bar + 8 * s, SPLIT_THREADS);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    mbar_init(done_bar, 1);
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -379,106 +394,130 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int half = blockIdx.x % p.halves;
+  const int subset = blockIdx.x / p.halves, subsets = gridDim.x / p.halves;
   const int64_t blocks = (p.m + WG_ROWS - 1) / WG_ROWS;
-  const uint32_t dy_bytes = uint32_t(p.n) * WG_ROWS * 4, x_bytes = uint32_t(p.k) * WG_ROWS * 4;
-  const int halves = p.n / BM;
+  const int64_t my_blocks = blocks > subset ? (blocks - subset + subsets - 1) / subsets : 0;
+  const uint32_t x_bytes = uint32_t(p.k) * WG_ROWS * 4;
 
   if (warp == 0) {
     if (lane == 0) {
       WgPipe pipe;
-      for (int64_t b = blockIdx.x; b < blocks; b += gridDim.x) {
+      for (int64_t i = 0; i < my_blocks; ++i) {
+        const int row0 = int((subset + i * subsets) * WG_ROWS);
         mbar_wait(empty_bar + 8 * pipe.stage, pipe.phase ^ 1);
         uint8_t* st = smem + pipe.stage * WG_STAGE_BYTES;
-        mbar_arrive_expect_tx(full_bar + 8 * pipe.stage, dy_bytes + x_bytes);
-        tma_load_3d(smem_u32(st), &map_dy, 0, int(b * WG_ROWS), 0, full_bar + 8 * pipe.stage);
-        tma_load_3d(smem_u32(st + 2 * WG_OP_BYTES), &map_x, 0, int(b * WG_ROWS), 0, full_bar + 8 * pipe.stage);
+        mbar_arrive_expect_tx(full_bar + 8 * pipe.stage, WG_DY_BYTES + x_bytes);
+        tma_load_3d(smem_u32(st), &map_dy, 0, row0, half * 4, full_bar + 8 * pipe.stage);
+        tma_load_3d(smem_u32(st + 2 * WG_DY_BYTES), &map_x, 0, row0, 0, full_bar + 8 * pipe.stage);
         pipe.advance();
       }
     }
   } else if (warp == 1) {
     WgPipe pipe;
     const uint32_t idesc = instr_desc_tf32_mn(p.k);
-    bool first = true;
-    for (int64_t b = blockIdx.x; b < blocks; b += gridDim.x) {
+    const uint32_t d_main = tmem_base, d_cross = tmem_base + WG_MAX_K;
+    uint32_t flush_phase = 0;
+    for (int64_t i = 0; i < my_blocks; ++i) {
+      const int in_chain = int(i % WG_FLUSH);
+      if (in_chain == 0) {
+        mbar_wait(tempty_bar, flush_phase ^ 1);   // previous chain drained by the epilogue warps
+        tc_fence_after();
+      }
       mbar_wait(ready_bar + 8 * pipe.stage, pipe.phase);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t st = smem_u32(smem + pipe.stage * WG_STAGE_BYTES);
 #pragma unroll
         for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
-          const uint64_t b_hi = smem_desc_mn_sw128(st + 2 * WG_OP_BYTES + ks * 1024);
-          const uint64_t b_lo = smem_desc_mn_sw128(st + 3 * WG_OP_BYTES + ks * 1024);
-          for (int h = 0; h < halves; ++h) {
-            const uint32_t a_off = uint32_t(h * 4 * WG_GROUP_BYTES + ks * 1024);
-            const uint64_t a_hi = smem_desc_mn_sw128(st + a_off), a_lo = smem_desc_mn_sw128(st + WG_OP_BYTES + a_off);
-            const uint32_t d = tmem_base + uint32_t(h * WG_MAX_COLS);
-            umma_tf32(d, a_lo, b_hi, idesc, (first && ks == 0) ? 0u : 1u);
-            umma_tf32(d, a_hi, b_lo, idesc, 1);
-            umma_tf32(d, a_hi, b_hi, idesc, 1);
-          }
+          const uint64_t a_hi = smem_desc_mn_sw128(st + ks * 1024), a_lo = smem_desc_mn_sw128(st + WG_DY_BYTES + ks * 1024);
+          const uint64_t b_hi = smem_desc_mn_sw128(st + 2 * WG_DY_BYTES + ks * 1024);
+          const uint64_t b_lo = smem_desc_mn_sw128(st + 2 * WG_DY_BYTES + WG_X_BYTES + ks * 1024);
+          const uint32_t accum = (in_chain | ks) != 0;
+          umma_tf32(d_cross, a_lo, b_hi, idesc, accum);
+          umma_tf32(d_cross, a_hi, b_lo, idesc, 1);
+          umma_tf32(d_main, a_hi, b_hi, idesc, accum);
         }
         umma_commit(empty_bar + 8 * pipe.stage);
+        if (in_chain == WG_FLUSH - 1 || i == my_blocks - 1) umma_commit(tfull_bar);
       }
       __syncwarp();
-      first = false;
+      if (in_chain == WG_FLUSH - 1) flush_phase ^= 1;
       pipe.advance();
     }
-    if (lane == 0) umma_commit(done_bar);
-    __syncwarp();
   } else if (warp >= 8) {
-    // split hi/lo; threads own a fixed (group, 16-byte chunk) pair so that dY column sums stay in registers
+    // split hi/lo; a thread owns one (32-column group, 16-byte chunk, 8-row half) item of dY or X, so the dY
+    // column sums stay in its registers
     WgPipe pipe;
     const int tid = threadIdx.x - 256;
-    const int dy_pairs = p.n / 4, x_pairs = p.k / 4;
+    const int dy_items = (BM / 4) * 2, x_items = (p.k / 4) * 2;   // 64 + up to 128 <= 256 threads
+    const bool active = tid < dy_items + x_items;
+    const bool is_dy = tid < dy_items;
+    const int item = is_dy ? tid : tid - dy_items;
+    const int pair = item >> 1, r0 = (item & 1) * 8;
+    const int c = pair & 7;
+    const uint32_t op_off = (is_dy ? 0u : uint32_t(2 * WG_DY_BYTES)) + uint32_t(pair >> 3) * WG_GROUP_BYTES;
+    const uint32_t lo_off = is_dy ? uint32_t(WG_DY_BYTES) : uint32_t(WG_X_BYTES);
     float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t b = blockIdx.x; b < blocks; b += gridDim.x) {
+    for (int64_t i = 0; i < my_blocks; ++i) {
       mbar_wait(full_bar + 8 * pipe.stage, pipe.phase);
-      uint8_t* st = smem + pipe.stage * WG_STAGE_BYTES;
-      for (int pr = tid; pr < dy_pairs + x_pairs; pr += 128) {
-        const bool is_dy = pr < dy_pairs;
-        const int q = is_dy ? pr : pr - dy_pairs;
-        uint8_t* base = st + (is_dy ? 0 : 2 * WG_OP_BYTES) + (q >> 3) * WG_GROUP_BYTES;
-        const int c = q & 7;
-#pragma unroll 4
-        for (int r = 0; r < WG_ROWS; ++r) {
+      if (active) {
+        uint8_t* base = smem + pipe.stage * WG_STAGE_BYTES + op_off;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = r0 + rr;
           uint8_t* hi_p = base + r * 128 + (((((c >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4);
           const float4 v = *reinterpret_cast<const float4*>(hi_p);
           float4 h, l;
           h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
           l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
           *reinterpret_cast<float4*>(hi_p) = h;
-          *reinterpret_cast<float4*>(hi_p + WG_OP_BYTES) = l;
-          if (is_dy && pr == tid) { colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w; }
+          *reinterpret_cast<float4*>(hi_p + lo_off) = l;
+          colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w;
         }
       }
       fence_proxy_async();
       mbar_arrive(ready_bar + 8 * pipe.stage);
       pipe.advance();
     }
-    if (p.partial_b && tid < dy_pairs) {
+    if (p.partial_b && is_dy) {
       // logical chunk c of group g covers columns g*32 + 4c .. +3 (the swizzle only permutes positions)
-      *reinterpret_cast<float4*>(p.partial_b + int64_t(blockIdx.x) * p.n + (tid >> 3) * 32 + (tid & 7) * 4) = colsum;
+      float* dst = p.partial_b + int64_t(subset * 2 + (item & 1)) * p.n + half * BM + (pair >> 3) * 32 + c * 4;
+      *reinterpret_cast<float4*>(dst) = colsum;
     }
   } else if (warp >= 4) {
     const int quad = warp - 4;
-    mbar_wait(done_bar, 0);
-    tc_fence_after();
-    float* out = p.partial_w + int64_t(blockIdx.x) * p.n * p.k;
-    for (int h = 0; h < halves; ++h) {
-      const int row = h * BM + quad * 32 + lane;
-      for (int c0 = 0; c0 < p.k; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(h * WG_MAX_COLS + c0), r);
-        float* dst = out + int64_t(row) * p.k + c0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-      }
+    const int row = half * BM + quad * 32 + lane;
+    float* out = p.partial_w + (int64_t(subset) * p.n + row) * p.k;
+    const int64_t chains = (my_blocks + WG_FLUSH - 1) / WG_FLUSH;
+    uint32_t phase = 0;
+    if (chains == 0) {
+      for (int c0 = 0; c0 < p.k; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    tc_fence_before();
+    for (int64_t ch = 0; ch < chains; ++ch) {
+      mbar_wait(tfull_bar, phase);
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.k; c0 += 32) {
+        uint32_t r[32], rc[32];
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(WG_MAX_K + c0), rc);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]) + __uint_as_float(rc[j]), __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]),
+                                 __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]), __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]));
+          float4* dst = reinterpret_cast<float4*>(out + c0 + j);
+          if (ch > 0) {
+            const float4 o = *dst;
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *dst = v;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar);
+      phase ^= 1;
+    }
   }
-  (void)bias_s;
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -571,12 +610,12 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
 }
 
 // row-major fp32 [rows, cols] viewed as [cols/32 groups][rows][32]: boxes of [groups, 16 rows, 32 cols]
-static int make_map_mn(CUtensorMap* map, const float* base, int64_t rows, int cols, int64_t ld) {
+static int make_map_mn(CUtensorMap* map, const float* base, int64_t rows, int cols, int64_t ld, int box_groups) {
   EncodeTiledFn fn = encode_tiled();
   PC_REQUIRE(fn, PC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[3] = {32, cuuint64_t(rows), cuuint64_t(cols / 32)};
   cuuint64_t gstride[2] = {cuuint64_t(ld) * 4, 128};
-  cuuint32_t box[3] = {32, WG_ROWS, cuuint32_t(cols / 32)};
+  cuuint32_t box[3] = {32, WG_ROWS, cuuint32_t(box_groups)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -586,26 +625,30 @@ static int make_map_mn(CUtensorMap* map, const float* base, int64_t rows, int co
 }
 
 extern "C" size_t pc_wgrad_workspace_bytes(int n, int k) {
-  return size_t(sm_count()) * (size_t(n) * k + size_t(n)) * sizeof(float);
+  return size_t(sm_count()) * (size_t(n) * k + 2 * size_t(n)) * sizeof(float);
 }
 
 extern "C" int pc_wgrad_tf32x3(const float* dy, int64_t m, int n, int64_t ld_dy, const float* x, int k, int64_t ld_x,
                                float* dw, float* db, void* workspace, size_t workspace_bytes, pc_stream_t stream) {
   PC_REQUIRE(m > 0, PC_ERR_INVALID, "wgrad: need at least one row");
   PC_REQUIRE(dy && x && dw && workspace, PC_ERR_INVALID, "wgrad: null pointer");
-  PC_REQUIRE((n == 128 || n == 256) && k >= 32 && k % 32 == 0 && k <= WG_MAX_COLS, PC_ERR_UNSUPPORTED,
-             "wgrad: n=%d must be 128 or 256 and k=%d a multiple of 32 up to 256", n, k);
+  PC_REQUIRE(n >= 128 && n % 128 == 0 && n <= 1024 && k >= 32 && k % 32 == 0 && k <= WG_MAX_K, PC_ERR_UNSUPPORTED,
+             "wgrad: n=%d must be a multiple of 128 and k=%d a multiple of 32 up to 256", n, k);
   PC_REQUIRE(ld_dy % 4 == 0 && ld_x % 4 == 0, PC_ERR_INVALID, "wgrad: leading dimensions must be multiples of 4 floats");
   PC_REQUIRE(workspace_bytes >= pc_wgrad_workspace_bytes(n, k), PC_ERR_WORKSPACE, "wgrad: workspace too small");
   const int64_t blocks = (m + WG_ROWS - 1) / WG_ROWS;
-  const int grid = int(blocks < sm_count() ? blocks : sm_count());
+  const int halves = n / BM;
+  int subsets = sm_count() / halves;
+  if (subsets < 1) subsets = 1;
+  if (blocks < subsets) subsets = int(blocks);
+  const int grid = subsets * halves;
   WgradParams p;
-  p.m = m; p.n = n; p.k = k;
+  p.m = m; p.n = n; p.k = k; p.halves = halves;
   p.partial_w = reinterpret_cast<float*>(workspace);
-  p.partial_b = db ? p.partial_w + size_t(grid) * n * k : nullptr;
+  p.partial_b = db ? p.partial_w + size_t(subsets) * n * k : nullptr;
   CUtensorMap map_dy, map_x;
-  if (int rc = make_map_mn(&map_dy, dy, m, n, ld_dy)) return rc;
-  if (int rc = make_map_mn(&map_x, x, m, k, ld_x)) return rc;
+  if (int rc = make_map_mn(&map_dy, dy, m, n, ld_dy, 4)) return rc;
+  if (int rc = make_map_mn(&map_x, x, m, k, ld_x, k / 32)) return rc;
   static bool configured = false;
   if (!configured) {
     PC_CUDA(cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
@@ -615,10 +658,10 @@ extern "C" int pc_wgrad_tf32x3(const float* dy, int64_t m, int n, int64_t ld_dy,
   wgrad_tf32x3_kernel<<<grid, GEMM_THREADS, WG_SMEM, st>>>(map_dy, map_x, p);
   PC_LAUNCH_CHECK();
   const int64_t nk = int64_t(n) * k;
-  reduce_partials_kernel<<<unsigned((nk + 255) / 256), 256, 0, st>>>(p.partial_w, grid, nk, dw);
+  reduce_partials_kernel<<<unsigned((nk + 255) / 256), 256, 0, st>>>(p.partial_w, subsets, nk, dw);
   PC_LAUNCH_CHECK();
   if (db) {
-    reduce_partials_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(p.partial_b, grid, n, db);
+    reduce_partials_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(p.partial_b, 2 * subsets, n, db);
     PC_LAUNCH_CHECK();
   }
   return PC_OK;
