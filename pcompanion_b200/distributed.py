@@ -1,0 +1,250 @@
+"""Node-partitioned Product2Vec over the GPUs of one box.
+
+The reference has no multi-GPU path at all; this is new.  Rank g owns the contiguous node range
+[bounds[g], bounds[g+1]): their features, FFN outputs, Q and K|V rows, and every CSR row (edge
+list of an aggregating node) of those nodes.  Columns are global ids; the K|V rows of columns
+owned by other ranks form the halo.  Per step:
+
+  forward   pack local K|V rows requested by peers (pc_rows_gather) -> all-to-all (NCCL over
+            NVLink, variable splits) -> GAT kernel over [local | halo] rows via a remapped CSR
+  backward  dK|dV partials of halo rows -> reverse all-to-all -> owner adds them in fixed peer
+            order (pc_rows_scatter_add: unique ids per peer => deterministic, no float atomics)
+  weights   replicated; gradients all-reduced (sum) before the optimiser step
+
+``HaloPlan`` holds only index logic and the collectives, so it runs on any backend (the
+world_size-2 ``gloo`` tests drive it on CPU tensors); all row movement and arithmetic on the
+product path is CUDA.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class HaloPlan:
+    """Which rows every rank sends / receives, and the CSR remapped to [local | halo] column space."""
+
+    def __init__(self, rowptr: torch.Tensor, col_global: torch.Tensor, bounds: List[int], rank: int, group=None):
+        self.group = group
+        self.rank = rank
+        self.world = len(bounds) - 1
+        self.bounds = list(bounds)
+        dev = col_global.device
+        base, end = bounds[rank], bounds[rank + 1]
+        self.n_local = end - base
+        col = col_global.to(torch.int64)
+        uniq = self._unique_sorted(col)
+        remote = uniq[(uniq < base) | (uniq >= end)]                  # ascending => grouped by owner
+        bnd = torch.tensor(bounds, dtype=torch.int64, device=dev)
+        owner_pos = torch.searchsorted(remote, bnd)                   # remote[owner_pos[p]:owner_pos[p+1]] live on rank p
+        self.recv_counts = (owner_pos[1:] - owner_pos[:-1]).tolist()  # rows I receive from each peer
+        self.n_halo = int(remote.numel())
+        # tell every owner which of its rows I need
+        counts_out = torch.tensor(self.recv_counts, dtype=torch.int64, device=dev)
+        counts_in = torch.empty_like(counts_out)
+        self._a2a(counts_in, counts_out, None, None)
+        self.send_counts = counts_in.tolist()                         # rows I send to each peer
+        want = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=dev)
+        self._a2a(want, remote.contiguous(), self.send_counts, self.recv_counts)
+        self.send_idx = (want - base).contiguous()                    # local row ids, grouped by destination peer
+        # remap columns: local -> [0, n_local), remote -> n_local + position in `remote`
+        is_local = (col >= base) & (col < end)
+        ext = torch.where(is_local, col - base, self.n_local + torch.searchsorted(remote, col))
+        self.graph = ops.CSRGraph(rowptr.contiguous(), ext.to(torch.int32).contiguous(), self.n_local,
+                                  self.n_local + self.n_halo) if col.is_cuda else None
+        self.col_ext = ext
+        self.rowptr = rowptr
+
+    @staticmethod
+    def _unique_sorted(col: torch.Tensor) -> torch.Tensor:
+        if col.is_cuda:   # same radix sort + unique kernels as the BPG build
+            keys = col.clone()
+            top = int(col.max().item()) + 1 if col.numel() else 1
+            nbytes = max(1, ((max(top, 2) - 1).bit_length() + 7) // 8)
+            ops.sort_keys_(keys, (1 << nbytes) - 1)
+            return ops.unique_sorted(keys)
+        return torch.unique(col)
+
+    def _a2a(self, out, inp, out_splits, in_splits):
+        if self.world == 1:
+            out.copy_(inp)
+            return
+        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.group)
+
+    # rows travel as [n, width] fp32; splits are in rows
+    def forward_exchange(self, send_rows: torch.Tensor, recv_rows: torch.Tensor) -> None:
+        """send_rows = table[send_idx] (grouped by peer) -> recv_rows [n_halo, width] (grouped by owner)."""
+        self._a2a(recv_rows, send_rows, self.recv_counts, self.send_counts)
+
+    def reverse_exchange(self, halo_grads: torch.Tensor, returned: torch.Tensor) -> None:
+        """halo_grads [n_halo, width] -> returned [n_send, width], row i belongs to local row send_idx[i]."""
+        self._a2a(returned, halo_grads, self.send_counts, self.recv_counts)
+
+    def halo_bytes(self, width: int = 256) -> int:
+        return self.n_halo * width * 4
+
+
+class _HaloGather(torch.autograd.Function):
+    """[n_local, W] -> [n_local + n_halo, W]; backward returns the halo gradients to their owners."""
+
+    @staticmethod
+    def forward(ctx, table, plan: HaloPlan):
+        table = table.contiguous()
+        w = table.shape[1]
+        ext = torch.empty(plan.n_local + plan.n_halo, w, dtype=table.dtype, device=table.device)
+        ext[: plan.n_local].copy_(table)
+        send = ops.rows_gather(table, plan.send_idx)
+        plan.forward_exchange(send, ext[plan.n_local:])
+        ctx.plan = plan
+        return ext
+
+    @staticmethod
+    def backward(ctx, d_ext):
+        plan = ctx.plan
+        d_ext = d_ext.contiguous()
+        w = d_ext.shape[1]
+        d_local = d_ext[: plan.n_local].clone()
+        returned = torch.empty(plan.send_idx.numel(), w, dtype=d_ext.dtype, device=d_ext.device)
+        plan.reverse_exchange(d_ext[plan.n_local:].contiguous(), returned)
+        off = 0
+        for cnt in plan.send_counts:            # fixed peer order; ids are unique inside one peer's chunk
+            if cnt:
+                ops.rows_scatter_add_(d_local, plan.send_idx[off: off + cnt], returned[off: off + cnt])
+            off += cnt
+        return d_local, None
+
+
+def halo_gather(table: torch.Tensor, plan: HaloPlan) -> torch.Tensor:
+    return _HaloGather.apply(table, plan)
+
+
+def forward_graph_partitioned(model, x_local: torch.Tensor, plan: HaloPlan) -> torch.Tensor:
+    """Product2Vec.forward_graph on one partition: local FFN / projections, halo exchange of K|V,
+    attention over the remapped CSR, out-projection; rows without neighbours keep ffn(x)."""
+    from .dense import linear
+    h = model._ffn_rows(x_local)
+    w, b = model.attention.in_proj_weight, model.attention.in_proj_bias
+    e = w.shape[1]
+    q = linear(h, w[:e], b[:e])
+    kv = linear(h, w[e:], b[e:])
+    kv_ext = halo_gather(kv, plan)
+    p, seed = model._dropout_args()
+    o = ops.gat_attention(q, kv_ext, plan.graph, model.heads, p, seed)
+    out = linear(o, model.attention.out_proj.weight, model.attention.out_proj.bias)
+    has = (plan.graph.rowptr[1:] > plan.graph.rowptr[:-1]).unsqueeze(1)
+    return torch.where(has, out, h)
+
+
+def allreduce_gradients(model, group=None) -> None:
+    """Sum the replicated-weight gradients over the ranks (one flat all-reduce)."""
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off: off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+# ----------------------------------------------------------------------------- multi-GPU benchmark leg
+def run_partitioned_bench(args, rank: int, world: int, dev: torch.device) -> None:
+    """bench.py --gpus N (N > 1): weak scaling, 1 M nodes / ~20 M edges per GPU, columns uniform over
+    the global node range, so (N-1)/N of every rank's edges point at halo rows."""
+    import bench as B
+    import pcompanion_b200 as pc
+    from pcompanion_b200 import _lib
+    n_loc, e_loc = B.NODES_PER_GPU, B.EDGES_PER_GPU
+    n_total = n_loc * world
+    bounds = [i * n_loc for i in range(world + 1)]
+    g = torch.Generator(device=dev).manual_seed(B.SEED + 100 + rank)
+    rows = torch.randint(0, n_loc, (e_loc,), generator=g, device=dev, dtype=torch.int32)
+    cols = torch.randint(0, n_total, (e_loc,), generator=g, device=dev, dtype=torch.int32)
+    csr, _ = ops.build_csr(rows, cols, n_loc, n_total)
+    del rows, cols
+    plan = HaloPlan(csr.rowptr, csr.col, bounds, rank)
+    plan.graph.transposed()
+    e_local = csr.num_edges
+    x = torch.randn(n_loc, 128, generator=g, device=dev)
+    cfg = B.make_cfg(dev)
+    torch.manual_seed(B.SEED)                      # identical replicated weights on every rank
+    model = pc.Product2Vec(cfg).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+    trip = torch.randint(0, n_loc, (B.TRIPLETS, 2 + B.KNEG), generator=g, device=dev)
+    x_host, trip_host = x.cpu().pin_memory(), trip.cpu().pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(xd, tr):
+        emb = forward_graph_partitioned(model, xd, plan)
+        a, p = emb[tr[:, 0]], emb[tr[:, 1]]
+        ng = emb[tr[:, 2:].reshape(-1)].reshape(B.TRIPLETS, B.KNEG, -1)
+        loss = model.triplet_loss(a, p, ng)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_gradients(model)
+        opt.step()
+        return loss
+
+    def step_e2e():
+        xd = torch.empty_like(x); xd.copy_(x_host, non_blocking=True)
+        tr = torch.empty_like(trip); tr.copy_(trip_host, non_blocking=True)
+        loss_host.copy_(step(xd, tr).detach(), non_blocking=True)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize(); dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            out = fn()
+        ev1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1) / steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out
+
+    for _ in range(args.warmup):
+        step(x, trip)
+    sampler = B.ClockSampler(dev.index)
+    launches0 = _lib.LAUNCHES
+    ms, loss = timed(lambda: step(x, trip), args.steps)
+    launches = _lib.LAUNCHES - launches0
+    clocks = sampler.stop()
+    for _ in range(2):
+        step_e2e()
+    e2e_ms, _ = timed(step_e2e, args.steps)
+    tot = torch.tensor([e_local, plan.n_halo], dtype=torch.float64, device=dev)
+    dist.all_reduce(tot)
+    e_total, halo_total = tot.tolist()
+    if rank == 0:
+        peak, peak_src = B.measured_peaks()
+        algo = (3152 * e_local + 3676 * n_loc)
+        line = {
+            "metric": "gat_edges_per_sec_fwd_bwd", "value": e_total / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C5-style: node-partitioned synthetic BPG, {n_loc} products / ~{e_loc} co-view edges per GPU x {world} GPUs, "
+                                   "columns uniform over the global range, Product2Vec GAT fwd+bwd with NCCL all-to-all halo exchange of "
+                                   "K|V rows (fwd) and dK|dV partials (bwd), gradient all-reduce, Adam",
+                       "nodes_total": n_total, "edges_total": int(e_total), "halo_rows_per_gpu": int(halo_total / world),
+                       "halo_bytes_per_gpu_per_direction": int(halo_total / world) * 1024, "batchnorm": "per-rank batch statistics",
+                       "l2": "working set exceeds the 126 MB L2; no flush needed"},
+            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "whole step per GPU against the sparse-kernel algorithmic bytes (3152 B/edge + 3676 B/node); "
+                                 "the halo all-to-all moves halo_bytes over NVLink each way on top"},
+            "clocks": clocks,
+            "e2e": {"value": e_total / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": (x_host.numel() * 4 + trip_host.numel() * 8) * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches, "loss": float(loss.item()),
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()

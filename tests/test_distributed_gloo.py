@@ -1,0 +1,103 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: halo plan, forward / reverse exchange,
+gradient all-reduce and sharded top-K merge.  Compute is done by the oracle *in the test*; the
+product package is only asked for index logic and collectives."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _global_problem():
+    rng = np.random.default_rng(0)
+    n, w = 64, 256
+    deg = rng.poisson(5, n); deg[::9] = 0
+    rowptr = np.zeros(n + 1, np.int64); np.cumsum(deg, out=rowptr[1:])
+    col = np.concatenate([np.sort(rng.choice(n, d, replace=False)) for d in deg]).astype(np.int32)
+    q = rng.normal(size=(n, 128)); kv = rng.normal(size=(n, w)); d_o = rng.normal(size=(n, 128))
+    return n, rowptr, col, q, kv, d_o
+
+
+def _worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import p2v, retrieval as oret
+        from pcompanion_b200.distributed import HaloPlan, allreduce_gradients
+        n, rowptr, col, q, kv, d_o = _global_problem()
+        bounds = [0, 30, n]                                         # uneven partition
+        b0, b1 = bounds[rank], bounds[rank + 1]
+        lp = rowptr[b0:b1 + 1] - rowptr[b0]
+        lcol = col[rowptr[b0]:rowptr[b1]]
+        plan = HaloPlan(torch.tensor(lp), torch.tensor(lcol), bounds, rank)
+        assert plan.n_local == b1 - b0 and sum(plan.recv_counts) == plan.n_halo
+        # forward exchange of K|V rows
+        kv_loc = torch.tensor(kv[b0:b1])
+        recv = torch.empty(plan.n_halo, kv.shape[1], dtype=kv_loc.dtype)
+        plan.forward_exchange(kv_loc[plan.send_idx].contiguous(), recv)
+        kv_ext = torch.cat([kv_loc, recv]).numpy()
+        o, _ = p2v.gat_csr_forward(q[b0:b1], kv_ext, lp, plan.col_ext.numpy(), 4)
+        o_ref, _ = p2v.gat_csr_forward(q, kv, rowptr, col, 4)
+        assert np.array_equal(o, o_ref[b0:b1])                      # partitioned == single-process, bit for bit
+        # backward: halo dK|dV partials return to their owners, fixed peer order
+        dq, dkv_ext = p2v.gat_csr_backward(q[b0:b1], kv_ext, lp, plan.col_ext.numpy(), 4, d_o[b0:b1])
+        returned = torch.empty(plan.send_idx.numel(), kv.shape[1], dtype=torch.float64)
+        plan.reverse_exchange(torch.tensor(dkv_ext[plan.n_local:]).contiguous(), returned)
+        dkv_loc = torch.tensor(dkv_ext[:plan.n_local]).clone()
+        off = 0
+        for cnt in plan.send_counts:
+            idx = plan.send_idx[off:off + cnt]
+            assert idx.unique().numel() == cnt                      # unique per peer => deterministic scatter-add
+            dkv_loc.index_add_(0, idx, returned[off:off + cnt]); off += cnt
+        dq_ref, dkv_ref = p2v.gat_csr_backward(q, kv, rowptr, col, 4, d_o)
+        np.testing.assert_allclose(dq, dq_ref[b0:b1], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(dkv_loc.numpy(), dkv_ref[b0:b1], rtol=1e-12, atol=1e-12)
+        # replicated-weight gradient all-reduce
+        lin = torch.nn.Linear(4, 3)
+        for p in lin.parameters():
+            p.grad = torch.full_like(p, float(rank + 1))
+        allreduce_gradients(lin)
+        assert all(torch.all(p.grad == 3.0) for p in lin.parameters())
+        # sharded retrieval: per-shard top-K, all-gather, merge (ties -> lowest global index)
+        rng = np.random.default_rng(1)
+        cat = rng.normal(size=(500, 128)).astype(np.float32); cat[rng.integers(0, 500, 100)] = cat[3]
+        tid = rng.integers(0, 5, 500).astype(np.int32)
+        qq = rng.normal(size=(6, 128)).astype(np.float32); qq[0] = cat[3]
+        rt = rng.integers(0, 5, 6).astype(np.int32)
+        sb = [0, 210, 500]
+        s, i = oret.masked_topk(qq, cat[sb[rank]:sb[rank + 1]], 10, rt, tid[sb[rank]:sb[rank + 1]], index_base=sb[rank])
+        gs = [torch.empty(6, 10, dtype=torch.float64) for _ in range(world)]
+        gi = [torch.empty(6, 10, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(gs, torch.tensor(s)); dist.all_gather(gi, torch.tensor(i))
+        ms, mi = oret.merge_topk(torch.cat(gs, 1).numpy(), torch.cat(gi, 1).numpy(), 10)
+        fs, fi = oret.masked_topk(qq, cat, 10, rt, tid)
+        assert np.array_equal(mi, fi) and np.array_equal(ms, fs)
+        results[rank] = "ok"
+    except Exception as e:  # pragma: no cover
+        import traceback
+        results[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_plan_exchange_and_shard_merge_world2():
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert all(results.get(r) == "ok" for r in range(world)), dict(results)
+
+
+def test_halo_plan_single_rank_is_identity():
+    from pcompanion_b200.distributed import HaloPlan
+    n, rowptr, col, *_ = _global_problem()
+    plan = HaloPlan(torch.tensor(rowptr), torch.tensor(col), [0, n], 0)
+    assert plan.n_halo == 0 and plan.send_idx.numel() == 0
+    assert np.array_equal(plan.col_ext.numpy(), col.astype(np.int64))

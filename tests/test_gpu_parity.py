@@ -325,7 +325,9 @@ def test_forward_graph_train_matches_oracle_and_torch_port_grads():
     (torch.stack(rows) * torch.tensor(w, dtype=torch.float64)).sum().backward()
     close(xt.grad, x64.grad.numpy(), rel=5e-5, what="dx")
     for (k, v), (_, v64) in zip(m.named_parameters(), pm.named_parameters()):
-        close(v.grad, v64.grad.numpy(), rel=5e-5, atol=1e-7, what="grad " + k)
+        # ffn.0.bias sits in front of BatchNorm: its gradient is mathematically zero (sum of 150 terms that
+        # cancel), both sides hold fp32 summation noise of ~1e-6 there
+        close(v.grad, v64.grad.numpy(), rel=5e-5, atol=3e-6 if k == "ffn.0.bias" else 1e-7, what="grad " + k)
 
 
 # ----------------------------------------------------------------------------- (3) losses / PCompanion
