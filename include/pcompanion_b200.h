@@ -93,17 +93,20 @@ int pc_csr_transpose_keys(const int64_t* rowptr, const int32_t* col, int64_t n_r
  *   counter-based hash of (seed, dst, src, head), regenerated in the backward kernels.
  * embed dim is 128 (config.py:8); heads in {1,2,4,8}.  All three kernels are deterministic
  * (fixed summation order per row, no float atomics). */
-int pc_gat_fwd(const float* q, const float* kv, const int64_t* rowptr, const int32_t* col, int64_t n_dst,
+/* q, d_o, dq and dkv carry a row stride in floats (ld_*), so Q and dO can be the two halves of one
+ * [n, 256] buffer (one 1 KiB gather per edge in the src-major backward) and dQ | dK|dV the
+ * column blocks of one [n, 384] buffer (a single K=384 dgrad GEMM for the packed in-projection). */
+int pc_gat_fwd(const float* q, int64_t ld_q, const float* kv, const int64_t* rowptr, const int32_t* col, int64_t n_dst,
                int heads, float dropout_p, uint64_t seed, float* o, float* stats, pc_stream_t stream);
 /* dst-major backward: dq [n_dst,128]; fills stats[:,1,:]. */
-int pc_gat_bwd_dst(const float* q, const float* kv, const int64_t* rowptr, const int32_t* col, int64_t n_dst,
-                   int heads, float dropout_p, uint64_t seed, const float* o, const float* d_o, float* stats,
-                   float* dq, pc_stream_t stream);
+int pc_gat_bwd_dst(const float* q, int64_t ld_q, const float* kv, const int64_t* rowptr, const int32_t* col,
+                   int64_t n_dst, int heads, float dropout_p, uint64_t seed, const float* o, const float* d_o,
+                   int64_t ld_do, float* stats, float* dq, int64_t ld_dq, pc_stream_t stream);
 /* src-major backward over the CSC (colptr [n_src+1], row [E] = dst ids per src, ascending):
  * dkv [n_src, 256]. */
-int pc_gat_bwd_src(const float* q, const float* kv, const int64_t* colptr, const int32_t* row, int64_t n_src,
-                   int heads, float dropout_p, uint64_t seed, const float* d_o, const float* stats, float* dkv,
-                   pc_stream_t stream);
+int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, const int64_t* colptr, const int32_t* row,
+                   int64_t n_src, int heads, float dropout_p, uint64_t seed, const float* d_o, int64_t ld_do,
+                   const float* stats, float* dkv, int64_t ld_dkv, pc_stream_t stream);
 
 /* Dense row projection on the tensor cores (tcgen05, 3xTF32 split => fp32-faithful, see gemm.cu):
  *   Y[m, n] = epilogue( A[m, k] . W[n, k]^T + bias[n] )
@@ -113,7 +116,8 @@ int pc_gat_bwd_src(const float* q, const float* kv, const int64_t* colptr, const
  * n % 32 == 0, n <= 768.  Columns [0, split) go to out0 (ld0), [split, n) to out1 (ld1) - the
  * Q | K|V outputs of the packed in-projection.  epilogue: 0 bias, 1 tanh(. + bias),
  * 2 (. + bias) * (1 - aux^2) (gradient through tanh, aux = tanh output),
- * 3 row r keeps (. + bias) if rowptr[r+1] > rowptr[r] else takes aux[r, :] (product2vec.py:76). */
+ * 3 row r keeps (. + bias) if rowptr[r+1] > rowptr[r] else takes aux[r, :] (product2vec.py:76),
+ * 4 (. + bias) + aux. */
 int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, const float* bias,
                      int epilogue, const float* aux, int64_t ld_aux, const int64_t* rowptr, float* out0, int64_t ld0,
                      int split, float* out1, int64_t ld1, pc_stream_t stream);
@@ -124,6 +128,23 @@ int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float*
 size_t pc_wgrad_workspace_bytes(int n, int k);
 int pc_wgrad_tf32x3(const float* dy, int64_t m, int n, int64_t ld_dy, const float* x, int k, int64_t ld_x, float* dw,
                     float* db, void* workspace, size_t workspace_bytes, pc_stream_t stream);
+
+/* BatchNorm1d + tanh of the FFN (product2vec.py:16-17) and the backward of the row select (:76).
+ * pc_col_stats: sums[0,c] = sum_r x[r,c], sums[1,c] = sum_r x[r,c]^2 (float64, fixed order) - the batch
+ *   statistics (and what SyncBN all-reduces).  pc_bn_bwd_reduce: sums[0,c] = sum_r dy, sums[1,c] =
+ *   sum_r dy * (x - mean) * rstd.  pc_scale_shift_tanh: y = [tanh](x * scale[c] + shift[c]).
+ * pc_affine2: out = ca[c] * a + cb[c] * b + cc[c] (BatchNorm input gradient with folded coefficients).
+ * pc_mask_split: rows with neighbours -> kept = g, rest = 0; rows without -> kept = 0, rest = g. */
+size_t pc_col_reduce_workspace_bytes(int n);
+int pc_col_stats(const float* x, int64_t m, int n, int64_t ldx, double* sums, void* workspace, size_t workspace_bytes,
+                 pc_stream_t stream);
+int pc_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* x, int64_t ldx, int64_t m, int n, const float* mean,
+                     const float* rstd, double* sums, void* workspace, size_t workspace_bytes, pc_stream_t stream);
+int pc_scale_shift_tanh(const float* x, int64_t ldx, int64_t m, int n, const float* scale, const float* shift,
+                        int apply_tanh, float* y, int64_t ldy, pc_stream_t stream);
+int pc_affine2(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int n, const float* ca,
+               const float* cb, const float* cc, float* out, int64_t ldo, pc_stream_t stream);
+int pc_mask_split(const float* g, int64_t m, int n, const int64_t* rowptr, float* kept, float* rest, pc_stream_t stream);
 
 /* ------------------------------------------------------------------ (3) hinge losses
  * Row hinge:  per[r] = max(0, margin - ||a_r - p_g + eps|| + mean_k ||a_r - n_{g,k} + eps||),

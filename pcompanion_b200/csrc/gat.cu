@@ -34,14 +34,14 @@ struct DropArgs {
 template <int H, int U, bool DROP>
 __global__ void __launch_bounds__(WARPS * 32)
 gat_fwd_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, const int64_t* __restrict__ rowptr,
-               const int32_t* __restrict__ col, int64_t n_dst, float scale_log2e, DropArgs drop,
+               const int32_t* __restrict__ col, int64_t n_dst, int64_t ldq4, float scale_log2e, DropArgs drop,
                float4* __restrict__ O, float* __restrict__ stats) {
   constexpr int G = 32 / H;
   const int lane = lane_id();
   const int64_t i = int64_t(blockIdx.x) * WARPS + warp_id();
   if (i >= n_dst) return;
   const int head = lane / G;
-  const float4 q = scale4(ldg4(Q + i * ROW4 + lane), scale_log2e);
+  const float4 q = scale4(ldg4(Q + i * ldq4 + lane), scale_log2e);
   const int64_t beg = rowptr[i], end = rowptr[i + 1];
   float m = -INFINITY, l = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -99,16 +99,16 @@ gat_fwd_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, cons
 template <int H, int U, bool DROP>
 __global__ void __launch_bounds__(WARPS * 32)
 gat_bwd_dst_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, const int64_t* __restrict__ rowptr,
-                   const int32_t* __restrict__ col, int64_t n_dst, float scale, DropArgs drop,
-                   const float4* __restrict__ O, const float4* __restrict__ dO, float* __restrict__ stats,
+                   const int32_t* __restrict__ col, int64_t n_dst, int64_t ldq4, int64_t lddo4, int64_t lddq4, float scale,
+                   DropArgs drop, const float4* __restrict__ O, const float4* __restrict__ dO, float* __restrict__ stats,
                    float4* __restrict__ dQ) {
   constexpr int G = 32 / H;
   const int lane = lane_id();
   const int64_t i = int64_t(blockIdx.x) * WARPS + warp_id();
   if (i >= n_dst) return;
   const int head = lane / G;
-  const float4 q = scale4(ldg4(Q + i * ROW4 + lane), scale * LOG2E);
-  const float4 go = ldg4(dO + i * ROW4 + lane);
+  const float4 q = scale4(ldg4(Q + i * ldq4 + lane), scale * LOG2E);
+  const float4 go = ldg4(dO + i * lddo4 + lane);
   const float4 o = ldg4(O + i * ROW4 + lane);
   const float delta = group_sum<G>(dot4(go, o));
   const float lse2 = stats[i * (2 * H) + head];
@@ -142,14 +142,14 @@ gat_bwd_dst_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
       }
     }
   }
-  dQ[i * ROW4 + lane] = scale4(dq, scale);
+  dQ[i * lddq4 + lane] = scale4(dq, scale);
 }
 
 template <int H, int U, bool DROP>
 __global__ void __launch_bounds__(WARPS * 32)
 gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, const int64_t* __restrict__ colptr,
-                   const int32_t* __restrict__ row, int64_t n_src, float scale, DropArgs drop,
-                   const float4* __restrict__ dO, const float* __restrict__ stats, float4* __restrict__ dKV) {
+                   const int32_t* __restrict__ row, int64_t n_src, int64_t ldq4, int64_t lddo4, int64_t lddkv4, float scale,
+                   DropArgs drop, const float4* __restrict__ dO, const float* __restrict__ stats, float4* __restrict__ dKV) {
   constexpr int G = 32 / H;
   const int lane = lane_id();
   const int64_t j = int64_t(blockIdx.x) * WARPS + warp_id();
@@ -173,8 +173,8 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
           dst[u] = __shfl_sync(FULL, my_row, (t + u) & 31);
           if (t + u < cnt) {
             const int64_t i = dst[u];
-            qi[u] = ldg4(Q + i * ROW4 + lane);
-            gi[u] = ldg4(dO + i * ROW4 + lane);
+            qi[u] = ldg4(Q + i * ldq4 + lane);
+            gi[u] = ldg4(dO + i * lddo4 + lane);
             lse2[u] = __ldg(stats + i * (2 * H) + head);
             delta[u] = __ldg(stats + i * (2 * H) + H + head);
           }
@@ -201,8 +201,8 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
     }
     dk = scale4(dk, scale);
   }
-  dKV[j * KV4 + lane] = dk;
-  dKV[j * KV4 + ROW4 + lane] = dv;
+  dKV[j * lddkv4 + lane] = dk;
+  dKV[j * lddkv4 + ROW4 + lane] = dv;
 }
 
 DropArgs make_drop(float p, uint64_t seed) {
@@ -239,9 +239,11 @@ constexpr int UNROLL = 4;
 
 using namespace pc;
 
-extern "C" int pc_gat_fwd(const float* q, const float* kv, const int64_t* rowptr, const int32_t* col, int64_t n_dst,
-                          int heads, float dropout_p, uint64_t seed, float* o, float* stats, pc_stream_t stream) {
+extern "C" int pc_gat_fwd(const float* q, int64_t ld_q, const float* kv, const int64_t* rowptr, const int32_t* col,
+                          int64_t n_dst, int heads, float dropout_p, uint64_t seed, float* o, float* stats,
+                          pc_stream_t stream) {
   if (int rc = check_common(q, rowptr, o, stats, n_dst, heads, dropout_p)) return rc;
+  PC_REQUIRE(ld_q >= 128 && ld_q % 4 == 0, PC_ERR_INVALID, "gat_fwd: ld_q=%lld must be a multiple of 4 and >= 128", (long long)ld_q);
   if (n_dst == 0) return PC_OK;
   const float scale_log2e = sqrtf(1.f / float(128 / heads)) * LOG2E;
   const DropArgs drop = make_drop(dropout_p, seed);
@@ -250,7 +252,7 @@ extern "C" int pc_gat_fwd(const float* q, const float* kv, const int64_t* rowptr
 #define CALL_FWD                                                                                   \
   gat_fwd_kernel<H, UNROLL, DROP><<<grid, WARPS * 32, 0, st>>>(                                    \
       reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(kv), rowptr, col, n_dst, \
-      scale_log2e, drop, reinterpret_cast<float4*>(o), stats)
+      ld_q / 4, scale_log2e, drop, reinterpret_cast<float4*>(o), stats)
   if (dropout_p > 0.f) {
     PC_DISPATCH_HEADS(heads, true, CALL_FWD)
   } else {
@@ -261,11 +263,14 @@ extern "C" int pc_gat_fwd(const float* q, const float* kv, const int64_t* rowptr
   return PC_OK;
 }
 
-extern "C" int pc_gat_bwd_dst(const float* q, const float* kv, const int64_t* rowptr, const int32_t* col,
+extern "C" int pc_gat_bwd_dst(const float* q, int64_t ld_q, const float* kv, const int64_t* rowptr, const int32_t* col,
                               int64_t n_dst, int heads, float dropout_p, uint64_t seed, const float* o,
-                              const float* d_o, float* stats, float* dq, pc_stream_t stream) {
+                              const float* d_o, int64_t ld_do, float* stats, float* dq, int64_t ld_dq,
+                              pc_stream_t stream) {
   if (int rc = check_common(q, rowptr, o, stats, n_dst, heads, dropout_p)) return rc;
   PC_REQUIRE(n_dst == 0 || (d_o && dq), PC_ERR_INVALID, "gat_bwd_dst: null pointer argument");
+  PC_REQUIRE(ld_q >= 128 && ld_q % 4 == 0 && ld_do >= 128 && ld_do % 4 == 0 && ld_dq >= 128 && ld_dq % 4 == 0, PC_ERR_INVALID,
+             "gat_bwd_dst: leading dimensions must be multiples of 4 and >= 128");
   if (n_dst == 0) return PC_OK;
   const float scale = sqrtf(1.f / float(128 / heads));
   const DropArgs drop = make_drop(dropout_p, seed);
@@ -273,7 +278,8 @@ extern "C" int pc_gat_bwd_dst(const float* q, const float* kv, const int64_t* ro
   cudaStream_t st = as_stream(stream);
 #define CALL_BD                                                                                          \
   gat_bwd_dst_kernel<H, UNROLL, DROP><<<grid, WARPS * 32, 0, st>>>(                                      \
-      reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(kv), rowptr, col, n_dst, scale, \
+      reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(kv), rowptr, col, n_dst,       \
+      ld_q / 4, ld_do / 4, ld_dq / 4, scale,                                                             \
       drop, reinterpret_cast<const float4*>(o), reinterpret_cast<const float4*>(d_o), stats,             \
       reinterpret_cast<float4*>(dq))
   if (dropout_p > 0.f) {
@@ -286,10 +292,12 @@ extern "C" int pc_gat_bwd_dst(const float* q, const float* kv, const int64_t* ro
   return PC_OK;
 }
 
-extern "C" int pc_gat_bwd_src(const float* q, const float* kv, const int64_t* colptr, const int32_t* row,
-                              int64_t n_src, int heads, float dropout_p, uint64_t seed, const float* d_o,
-                              const float* stats, float* dkv, pc_stream_t stream) {
+extern "C" int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, const int64_t* colptr, const int32_t* row,
+                              int64_t n_src, int heads, float dropout_p, uint64_t seed, const float* d_o, int64_t ld_do,
+                              const float* stats, float* dkv, int64_t ld_dkv, pc_stream_t stream) {
   if (int rc = check_common(kv, colptr, dkv, stats, n_src, heads, dropout_p)) return rc;
+  PC_REQUIRE(ld_q >= 128 && ld_q % 4 == 0 && ld_do >= 128 && ld_do % 4 == 0 && ld_dkv >= 256 && ld_dkv % 4 == 0, PC_ERR_INVALID,
+             "gat_bwd_src: leading dimensions must be multiples of 4 (q, d_o >= 128, dkv >= 256)");
   if (n_src == 0) return PC_OK;
   const float scale = sqrtf(1.f / float(128 / heads));
   const DropArgs drop = make_drop(dropout_p, seed);
@@ -297,7 +305,8 @@ extern "C" int pc_gat_bwd_src(const float* q, const float* kv, const int64_t* co
   cudaStream_t st = as_stream(stream);
 #define CALL_BS                                                                                          \
   gat_bwd_src_kernel<H, UNROLL, DROP><<<grid, WARPS * 32, 0, st>>>(                                      \
-      reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(kv), colptr, row, n_src, scale, \
+      reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(kv), colptr, row, n_src,       \
+      ld_q / 4, ld_do / 4, ld_dkv / 4, scale,                                                            \
       drop, reinterpret_cast<const float4*>(d_o), stats, reinterpret_cast<float4*>(dkv))
   if (dropout_p > 0.f) {
     PC_DISPATCH_HEADS(heads, true, CALL_BS)

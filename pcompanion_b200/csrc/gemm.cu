@@ -40,7 +40,7 @@ constexpr int SPLIT_THREADS = 256;      // warps 8-15
 constexpr int SMEM_MISC = 4096;         // barriers, tmem pointer, bias
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 + SMEM_MISC;
 
-enum Epilogue { EPI_BIAS = 0, EPI_BIAS_TANH = 1, EPI_TANH_GRAD = 2, EPI_BIAS_SELECT = 3 };
+enum Epilogue { EPI_BIAS = 0, EPI_BIAS_TANH = 1, EPI_TANH_GRAD = 2, EPI_BIAS_SELECT = 3, EPI_BIAS_ADD = 4 };
 
 struct LinearParams {
   int64_t m;
@@ -289,6 +289,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               y = make_float4(y.x * (1.f - a.x * a.x), y.y * (1.f - a.y * a.y), y.z * (1.f - a.z * a.z), y.w * (1.f - a.w * a.w));
             } else if (p.epilogue == EPI_BIAS_SELECT) {
               if (!keep) y = *reinterpret_cast<const float4*>(aux + j);
+            } else if (p.epilogue == EPI_BIAS_ADD) {
+              const float4 a = *reinterpret_cast<const float4*>(aux + j);
+              y = make_float4(y.x + a.x, y.y + a.y, y.z + a.z, y.w + a.w);
             }
             *reinterpret_cast<float4*>(dst + j) = y;
           }
@@ -583,8 +586,9 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   PC_REQUIRE(n >= 32 && n % 32 == 0 && n <= 768, PC_ERR_UNSUPPORTED, "linear: n=%d must be a multiple of 32 in [32, 768]", n);
   PC_REQUIRE(split > 0 && split <= n && split % 32 == 0 && (split == n || out1), PC_ERR_INVALID, "linear: bad output split");
   PC_REQUIRE(lda % 4 == 0 && ld0 % 4 == 0 && (split == n || ld1 % 4 == 0), PC_ERR_INVALID, "linear: leading dimensions must be multiples of 4 floats");
-  PC_REQUIRE(epilogue >= EPI_BIAS && epilogue <= EPI_BIAS_SELECT, PC_ERR_INVALID, "linear: unknown epilogue %d", epilogue);
-  PC_REQUIRE((epilogue != EPI_TANH_GRAD && epilogue != EPI_BIAS_SELECT) || (aux && ld_aux % 4 == 0), PC_ERR_INVALID, "linear: epilogue needs aux");
+  PC_REQUIRE(epilogue >= EPI_BIAS && epilogue <= EPI_BIAS_ADD, PC_ERR_INVALID, "linear: unknown epilogue %d", epilogue);
+  PC_REQUIRE((epilogue != EPI_TANH_GRAD && epilogue != EPI_BIAS_SELECT && epilogue != EPI_BIAS_ADD) || (aux && ld_aux % 4 == 0),
+             PC_ERR_INVALID, "linear: epilogue needs aux");
   PC_REQUIRE(epilogue != EPI_BIAS_SELECT || rowptr, PC_ERR_INVALID, "linear: select epilogue needs rowptr");
   LinearParams p;
   p.m = m; p.n = n; p.k = k;

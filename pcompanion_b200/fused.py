@@ -1,0 +1,159 @@
+"""Whole Product2Vec graph layer as ONE autograd node over the C-ABI kernels.
+
+forward_graph (FFN -> BatchNorm+tanh -> FFN -> packed in-projection -> attention over the CSR ->
+out-projection -> "rows without neighbours keep ffn(x)") and its complete backward, with no
+PyTorch arithmetic on [N, .] tensors: every row-sized operation is a tcgen05 GEMM with a fused
+epilogue, a GAT kernel or one of the streaming kernels in csrc/norm.cu.  Buffers are laid out for
+the kernels rather than for autograd:
+
+* QG [N, 256] = Q | dO   -> the src-major backward gathers one contiguous 1 KiB row per edge
+* DQKV [N, 384] = dQ | dK|dV -> the in-projection's input / weight gradients are single GEMMs
+* tanh' of the FFN, the residual add of the un-attended rows and the row select live in GEMM epilogues
+
+Reference semantics: /root/reference/src/models/product2vec.py:14-29,60,70-81 (train or eval
+BatchNorm, attention dropout on the weights).  With a ``HaloPlan`` the same node runs on one
+partition of a node-partitioned graph (halo exchange of K|V rows forward, of dK|dV partials
+backward; BatchNorm statistics all-reduced = SyncBN).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+F32 = torch.float32
+
+
+def _allreduce_sums(sums: torch.Tensor, count: int, group, sync: bool):
+    if sync and dist.is_initialized() and dist.get_world_size(group) > 1:
+        buf = torch.cat([sums.reshape(-1), torch.tensor([float(count)], dtype=sums.dtype, device=sums.device)])
+        dist.all_reduce(buf, group=group)
+        return buf[:-1].reshape(sums.shape), int(round(buf[-1].item()))
+    return sums, count
+
+
+class _P2VGraphLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w0, b0, gamma, beta, w3, b3, w5, b5, w_in, b_in, w_o, b_o, cfg):
+        graph, plan = cfg["graph"], cfg.get("plan")
+        heads, p_drop, seed = cfg["heads"], cfg["dropout_p"], cfg["seed"]
+        training, eps, momentum = cfg["training"], cfg["eps"], cfg["momentum"]
+        group, sync_bn = cfg.get("group"), cfg.get("sync_bn", False)
+        run_mean, run_var = cfg["running_mean"], cfg["running_var"]     # buffers: updated in place, never differentiated
+        x = x.contiguous()
+        n = x.shape[0]
+        z1 = ops.linear_tc(x, w0, b0)
+        if training:
+            sums, count = _allreduce_sums(ops.col_stats(z1), n, group, sync_bn)
+            mean64 = sums[0] / count
+            var64 = (sums[1] / count - mean64 * mean64).clamp_(min=0.0)
+            if run_mean is not None:
+                with torch.no_grad():
+                    m_ = 0.1 if momentum is None else momentum
+                    run_mean.mul_(1 - m_).add_(mean64.to(F32), alpha=m_)
+                    run_var.mul_(1 - m_).add_((var64 * (count / max(count - 1, 1))).to(F32), alpha=m_)
+        else:
+            count = n
+            mean64, var64 = run_mean.double(), run_var.double()
+        rstd64 = torch.rsqrt(var64 + eps)
+        mean, rstd = mean64.to(F32), rstd64.to(F32)
+        scale = (gamma.double() * rstd64).to(F32)
+        shift = (beta.double() - mean64 * gamma.double() * rstd64).to(F32)
+        a1 = ops.scale_shift_tanh(z1, scale, shift, tanh=True)
+        a2 = ops.linear_tc(a1, w3, b3, ops.EPI_BIAS_TANH)
+        h = ops.linear_tc(a2, w5, b5)
+        qg = torch.empty(n, 256, dtype=F32, device=x.device)
+        n_ext = graph.n_cols
+        kv = torch.empty(n_ext, 256, dtype=F32, device=x.device)
+        ops.linear_tc(h, w_in, b_in, split=128, out0=qg[:, :128], out1=kv[:n])
+        if plan is not None:
+            plan.forward_exchange(ops.rows_gather(kv[:n], plan.send_idx), kv[n:])
+        o, stats = ops.gat_fwd_raw(qg[:, :128], kv, graph, heads, p_drop, seed)
+        emb = ops.linear_tc(o, w_o, b_o, ops.EPI_BIAS_SELECT, aux=h, rowptr=graph.rowptr)
+        ctx.save_for_backward(x, z1, a1, a2, h, qg, kv, o, stats, mean, rstd, gamma, w0, w3, w5, w_in, w_o)
+        ctx.cfg = dict(cfg, count=count)
+        return emb
+
+    @staticmethod
+    def backward(ctx, d_emb):
+        x, z1, a1, a2, h, qg, kv, o, stats, mean, rstd, gamma, w0, w3, w5, w_in, w_o = ctx.saved_tensors
+        cfg = ctx.cfg
+        graph, plan = cfg["graph"], cfg.get("plan")
+        heads, p_drop, seed, training = cfg["heads"], cfg["dropout_p"], cfg["seed"], cfg["training"]
+        group, sync_bn, count = cfg.get("group"), cfg.get("sync_bn", False), cfg["count"]
+        n = x.shape[0]
+        d_out, d_rest = ops.mask_split(d_emb, graph.rowptr)
+        # out-projection
+        ops.linear_tc(d_out, w_o.t().contiguous(), None, out0=qg[:, 128:])            # dO next to Q
+        dw_o, db_o = ops.wgrad_tc(d_out, o)
+        # attention
+        if plan is None:
+            dqkv = torch.empty(n, 384, dtype=F32, device=x.device)
+            ops.gat_bwd_raw(qg[:, :128], kv, graph, heads, p_drop, seed, o, qg[:, 128:], stats, dqkv[:, :128], dqkv[:, 128:])
+            dw_in, db_in = ops.wgrad_tc(dqkv, h)
+            d_h = ops.linear_tc(dqkv, w_in.t().contiguous(), None, ops.EPI_BIAS_ADD, aux=d_rest)
+        else:
+            dq = torch.empty(n, 128, dtype=F32, device=x.device)
+            dkv = torch.empty(graph.n_cols, 256, dtype=F32, device=x.device)
+            ops.gat_bwd_raw(qg[:, :128], kv, graph, heads, p_drop, seed, o, qg[:, 128:], stats, dq, dkv)
+            returned = torch.empty(plan.send_idx.numel(), 256, dtype=F32, device=x.device)
+            plan.reverse_exchange(dkv[n:], returned)
+            off = 0
+            for cnt in plan.send_counts:      # fixed peer order, unique ids per peer: deterministic
+                if cnt:
+                    ops.rows_scatter_add_(dkv, plan.send_idx[off: off + cnt], returned[off: off + cnt])
+                off += cnt
+            dw_q, db_q = ops.wgrad_tc(dq, h)
+            dw_kv, db_kv = ops.wgrad_tc(dkv[:n], h)
+            dw_in, db_in = torch.cat([dw_q, dw_kv]), torch.cat([db_q, db_kv])
+            w_in_t = w_in.t().contiguous()                                            # [128, 384]
+            d_h = ops.linear_tc(dq, w_in_t[:, :128].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_rest)
+            d_h = ops.linear_tc(dkv[:n], w_in_t[:, 128:].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_h)
+        # FFN
+        dw5, db5 = ops.wgrad_tc(d_h, a2)
+        d_p2 = ops.linear_tc(d_h, w5.t().contiguous(), None, ops.EPI_TANH_GRAD, aux=a2)
+        dw3, db3 = ops.wgrad_tc(d_p2, a1)
+        d_y = ops.linear_tc(d_p2, w3.t().contiguous(), None, ops.EPI_TANH_GRAD, aux=a1)
+        sums = ops.bn_bwd_reduce(d_y, z1, mean, rstd)
+        world = 1
+        if training:
+            sums, _ = _allreduce_sums(sums, 0, group, sync_bn)
+            if sync_bn and dist.is_initialized():
+                world = dist.get_world_size(group)
+        d_beta64, d_gamma64 = sums[0], sums[1]
+        g64, r64, m64 = gamma.double(), rstd.double(), mean.double()
+        if training:
+            ca = g64 * r64
+            cb = -(g64 * r64 * r64 * d_gamma64 / count)
+            cc = -cb * m64 - g64 * r64 * d_beta64 / count
+            d_z1 = ops.affine2(d_y, z1, ca.to(F32), cb.to(F32), cc.to(F32))
+        else:
+            d_z1 = ops.scale_shift_tanh(d_y, (g64 * r64).to(F32), torch.zeros_like(mean), tanh=False)
+        dw0, db0 = ops.wgrad_tc(d_z1, x)
+        dx = ops.linear_tc(d_z1, w0.t().contiguous(), None) if ctx.needs_input_grad[0] else None
+        # gamma / beta gradients are already global sums under SyncBN; the caller's gradient all-reduce sums over ranks
+        d_gamma = (d_gamma64 / world).to(F32)
+        d_beta = (d_beta64 / world).to(F32)
+        return (dx, dw0, db0, d_gamma, d_beta, dw3, db3, dw5, db5, dw_in, db_in, dw_o, db_o, None)
+
+
+def p2v_graph_layer(model, x: torch.Tensor, graph: ops.CSRGraph, plan=None, group=None, sync_bn: bool = False) -> torch.Tensor:
+    """Fused forward_graph of a pcompanion_b200.Product2Vec module (train or eval mode)."""
+    l0, bn, _, l3, _, l5 = model.ffn
+    att = model.attention
+    p_drop, seed = model._dropout_args()
+    if model.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    cfg = dict(graph=graph, plan=plan, heads=model.heads, dropout_p=p_drop, seed=seed, training=model.training, eps=bn.eps,
+               momentum=bn.momentum, group=group, sync_bn=sync_bn, running_mean=bn.running_mean, running_var=bn.running_var)
+    return _P2VGraphLayer.apply(x, l0.weight, l0.bias, bn.weight, bn.bias, l3.weight, l3.bias, l5.weight, l5.bias,
+                                att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias, cfg)
+
+
+def fused_supported(model, x: torch.Tensor) -> bool:
+    l0, bn, _, l3, _, l5 = model.ffn
+    return (x.is_cuda and x.dtype == F32 and x.dim() == 2 and l0.in_features == 128 and l0.out_features == 256
+            and l3.out_features == 256 and l5.out_features == 128 and bn.affine and bn.track_running_stats)

@@ -157,6 +157,34 @@ def regular_graph(batch: int, n_nbr: int, device) -> CSRGraph:
 
 
 # --------------------------------------------------------------------------- GAT
+def _f32_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda or t.dtype != F32 or t.stride(-1) != 1:
+        raise RuntimeError(f"{what}: expected a float32 CUDA tensor with unit column stride, got {t.dtype} on {t.device} "
+                           "(no CPU fallback)")
+    return _lib.c_void_p(t.data_ptr())
+
+
+def gat_fwd_raw(q: torch.Tensor, kv: torch.Tensor, graph: "CSRGraph", heads: int, dropout_p: float, seed: int):
+    """pc_gat_fwd; q may be a strided [n, 128] view.  Returns (o [n,128], stats [n,2,heads])."""
+    o = torch.empty(graph.n_rows, EMB, dtype=F32, device=q.device)
+    stats = torch.empty(graph.n_rows, 2, heads, dtype=F32, device=q.device)
+    call("pc_gat_fwd", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(graph.rowptr, I64, "rowptr"),
+         dev(graph.col, I32, "col"), graph.n_rows, heads, float(dropout_p), int(seed), dev(o, F32, "o"),
+         dev(stats, F32, "stats"), stream())
+    return o, stats
+
+
+def gat_bwd_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, o, d_o, stats, dq, dkv) -> None:
+    """pc_gat_bwd_dst + pc_gat_bwd_src; q, d_o, dq, dkv may be strided views (row strides are passed down)."""
+    call("pc_gat_bwd_dst", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(graph.rowptr, I64, "rowptr"),
+         dev(graph.col, I32, "col"), graph.n_rows, heads, float(dropout_p), int(seed), dev(o, F32, "o"),
+         _f32_cuda(d_o, "d_o"), d_o.stride(0), dev(stats, F32, "stats"), _f32_cuda(dq, "dq"), dq.stride(0), stream())
+    colptr, row = graph.transposed()
+    call("pc_gat_bwd_src", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(colptr, I64, "colptr"),
+         dev(row, I32, "row"), graph.n_cols, heads, float(dropout_p), int(seed), _f32_cuda(d_o, "d_o"), d_o.stride(0),
+         dev(stats, F32, "stats"), _f32_cuda(dkv, "dkv"), dkv.stride(0), stream())
+
+
 class _GATAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, kv, graph: CSRGraph, heads: int, dropout_p: float, seed: int):
@@ -166,11 +194,7 @@ class _GATAttention(torch.autograd.Function):
             raise ValueError(f"gat: q must be [n_dst,{EMB}] and kv [n_src,{2 * EMB}], got {tuple(q.shape)}, {tuple(kv.shape)}")
         if q.shape[0] != graph.n_rows or kv.shape[0] != graph.n_cols:
             raise ValueError("gat: q / kv row counts do not match the graph")
-        o = torch.empty_like(q)
-        stats = torch.empty(q.shape[0], 2, heads, dtype=F32, device=q.device)
-        call("pc_gat_fwd", dev(q, F32, "q"), dev(kv, F32, "kv"), dev(graph.rowptr, I64, "rowptr"),
-             dev(graph.col, I32, "col"), graph.n_rows, heads, float(dropout_p), int(seed), dev(o, F32, "o"),
-             dev(stats, F32, "stats"), stream())
+        o, stats = gat_fwd_raw(q, kv, graph, heads, dropout_p, seed)
         ctx.save_for_backward(q, kv, o, stats)
         ctx.graph, ctx.heads, ctx.dropout_p, ctx.seed = graph, heads, float(dropout_p), int(seed)
         return o
@@ -178,17 +202,10 @@ class _GATAttention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_o):
         q, kv, o, stats = ctx.saved_tensors
-        g = ctx.graph
         d_o = d_o.contiguous()
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
-        call("pc_gat_bwd_dst", dev(q, F32, "q"), dev(kv, F32, "kv"), dev(g.rowptr, I64, "rowptr"), dev(g.col, I32, "col"),
-             g.n_rows, ctx.heads, ctx.dropout_p, ctx.seed, dev(o, F32, "o"), dev(d_o, F32, "d_o"),
-             dev(stats, F32, "stats"), dev(dq, F32, "dq"), stream())
-        colptr, row = g.transposed()
-        call("pc_gat_bwd_src", dev(q, F32, "q"), dev(kv, F32, "kv"), dev(colptr, I64, "colptr"), dev(row, I32, "row"),
-             g.n_cols, ctx.heads, ctx.dropout_p, ctx.seed, dev(d_o, F32, "d_o"), dev(stats, F32, "stats"),
-             dev(dkv, F32, "dkv"), stream())
+        gat_bwd_raw(q, kv, ctx.graph, ctx.heads, ctx.dropout_p, ctx.seed, o, d_o, stats, dq, dkv)
         return dq, dkv, None, None, None, None
 
 
@@ -199,25 +216,27 @@ def gat_attention(q: torch.Tensor, kv: torch.Tensor, graph: CSRGraph, heads: int
 
 
 # --------------------------------------------------------------------------- dense projections (tcgen05)
-EPI_BIAS, EPI_BIAS_TANH, EPI_TANH_GRAD, EPI_BIAS_SELECT = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_TANH, EPI_TANH_GRAD, EPI_BIAS_SELECT, EPI_BIAS_ADD = 0, 1, 2, 3, 4
 
 
 def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
-              aux: Optional[torch.Tensor] = None, rowptr: Optional[torch.Tensor] = None, split: Optional[int] = None):
+              aux: Optional[torch.Tensor] = None, rowptr: Optional[torch.Tensor] = None, split: Optional[int] = None,
+              out0: Optional[torch.Tensor] = None, out1: Optional[torch.Tensor] = None):
     """epilogue(A . W^T + bias) on the tensor cores (pc_linear_tf32x3).  Returns one [m, n] tensor, or
-    ([m, split], [m, n - split]) when `split` is given."""
+    ([m, split], [m, n - split]) when `split` is given.  out0 / out1 may be preallocated (strided) views."""
     m, k = a.shape
     n = w.shape[0]
     if a.stride(1) != 1 or w.stride() != (k, 1):
         raise ValueError("linear_tc: A must have unit column stride and W must be contiguous [n, k]")
     split_ = n if split is None else split
-    out0 = torch.empty(m, split_, dtype=F32, device=a.device)
-    out1 = torch.empty(m, n - split_, dtype=F32, device=a.device) if split_ < n else None
-    if not a.is_cuda or a.dtype != F32:
-        raise RuntimeError(f"linear_tc: A must be a float32 CUDA tensor (got {a.dtype} on {a.device}); no CPU fallback")
-    call("pc_linear_tf32x3", _lib.c_void_p(a.data_ptr()), m, k, a.stride(0), dev(w, F32, "w"), n, dev(bias, F32, "bias"), epilogue, dev(aux, F32, "aux"),
-         aux.stride(0) if aux is not None else 0, dev(rowptr, I64, "rowptr"), dev(out0, F32, "out0"), split_, split_,
-         dev(out1, F32, "out1"), (n - split_), stream())
+    if out0 is None:
+        out0 = torch.empty(m, split_, dtype=F32, device=a.device)
+    if out1 is None and split_ < n:
+        out1 = torch.empty(m, n - split_, dtype=F32, device=a.device)
+    call("pc_linear_tf32x3", _f32_cuda(a, "a"), m, k, a.stride(0), dev(w, F32, "w"), n, dev(bias, F32, "bias"), epilogue,
+         _f32_cuda(aux, "aux") if aux is not None else None, aux.stride(0) if aux is not None else 0,
+         dev(rowptr, I64, "rowptr"), _f32_cuda(out0, "out0"), out0.stride(0), split_,
+         _f32_cuda(out1, "out1") if out1 is not None else None, out1.stride(0) if out1 is not None else 0, stream())
     return out0 if out1 is None else (out0, out1)
 
 
@@ -232,9 +251,60 @@ def wgrad_tc(dy: torch.Tensor, x: torch.Tensor, want_bias: bool = True):
     dw = torch.empty(n, k, dtype=F32, device=dy.device)
     db = torch.empty(n, dtype=F32, device=dy.device) if want_bias else None
     ws = _lib.workspace(_lib.LIB.pc_wgrad_workspace_bytes(n, k), dy.device)
-    call("pc_wgrad_tf32x3", _lib.c_void_p(dy.data_ptr()), m, n, dy.stride(0), _lib.c_void_p(x.data_ptr()), k, x.stride(0),
+    call("pc_wgrad_tf32x3", _f32_cuda(dy, "dy"), m, n, dy.stride(0), _f32_cuda(x, "x"), k, x.stride(0),
          dev(dw, F32, "dw"), dev(db, F32, "db"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
     return dw, db
+
+
+# --------------------------------------------------------------------------- BatchNorm / tanh / select kernels
+def _col_reduce_ws(n: int, device):
+    return _lib.workspace(_lib.LIB.pc_col_reduce_workspace_bytes(n), device)
+
+
+def col_stats(x: torch.Tensor) -> torch.Tensor:
+    """float64 [2, n]: column sums of x and of x^2 (fixed summation order)."""
+    m, n = x.shape
+    sums = torch.empty(2, n, dtype=F64, device=x.device)
+    ws = _col_reduce_ws(n, x.device)
+    call("pc_col_stats", _f32_cuda(x, "x"), m, n, x.stride(0), dev(sums, F64, "sums"), dev(ws, torch.uint8, "ws"),
+         ws.numel(), stream())
+    return sums
+
+
+def bn_bwd_reduce(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor) -> torch.Tensor:
+    """float64 [2, n]: sum_r dy and sum_r dy * (x - mean) * rstd."""
+    m, n = x.shape
+    sums = torch.empty(2, n, dtype=F64, device=x.device)
+    ws = _col_reduce_ws(n, x.device)
+    call("pc_bn_bwd_reduce", _f32_cuda(dy, "dy"), dy.stride(0), _f32_cuda(x, "x"), x.stride(0), m, n, dev(mean, F32, "mean"),
+         dev(rstd, F32, "rstd"), dev(sums, F64, "sums"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return sums
+
+
+def scale_shift_tanh(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, tanh: bool = True) -> torch.Tensor:
+    m, n = x.shape
+    y = torch.empty(m, n, dtype=F32, device=x.device)
+    call("pc_scale_shift_tanh", _f32_cuda(x, "x"), x.stride(0), m, n, dev(scale, F32, "scale"), dev(shift, F32, "shift"),
+         int(tanh), dev(y, F32, "y"), n, stream())
+    return y
+
+
+def affine2(a: torch.Tensor, b: torch.Tensor, ca: torch.Tensor, cb: torch.Tensor, cc: torch.Tensor) -> torch.Tensor:
+    """ca[c] * a + cb[c] * b + cc[c]."""
+    m, n = a.shape
+    out = torch.empty(m, n, dtype=F32, device=a.device)
+    call("pc_affine2", _f32_cuda(a, "a"), a.stride(0), _f32_cuda(b, "b"), b.stride(0), m, n, dev(ca, F32, "ca"),
+         dev(cb, F32, "cb"), dev(cc, F32, "cc"), dev(out, F32, "out"), n, stream())
+    return out
+
+
+def mask_split(g: torch.Tensor, rowptr: torch.Tensor):
+    """(kept, rest): rows with neighbours keep g in `kept`, rows without in `rest` (zeros elsewhere)."""
+    g = g.contiguous()
+    kept, rest = torch.empty_like(g), torch.empty_like(g)
+    call("pc_mask_split", dev(g, F32, "g"), g.shape[0], g.shape[1], dev(rowptr, I64, "rowptr"), dev(kept, F32, "kept"),
+         dev(rest, F32, "rest"), stream())
+    return kept, rest
 
 
 # --------------------------------------------------------------------------- hinge losses

@@ -23,6 +23,7 @@ import torch.nn as nn
 
 from . import ops
 from .dense import ffn_forward, linear
+from .fused import fused_supported, p2v_graph_layer
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> None:
@@ -114,6 +115,8 @@ class Product2Vec(nn.Module):
         attention over the CSR, out-proj; nodes without out-neighbours keep ffn(x)
         (product2vec.py:76 / :98).  double_ffn_query=True is generate_all_embeddings' ffn(ffn(x)) query."""
         _require_cuda(x, "forward_graph")
+        if not double_ffn_query and fused_supported(self, x):
+            return p2v_graph_layer(self, x, graph)          # one autograd node, every row-sized op in a C-ABI kernel
         h = self._ffn_rows(x)
         hq = self._ffn_rows(h) if double_ffn_query else h
         out = self._attend(hq, h, graph)

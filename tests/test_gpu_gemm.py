@@ -119,3 +119,35 @@ def test_linear_autograd_function_matches_torch_autograd():
         ((torch.tanh(y) if tanh else y) * up.double()).sum().backward()
         for a, r, nm in zip(got, (x64, w64, b64), ("dx", "dw", "db")):
             close(a, r.grad.cpu().numpy(), what=f"{nm} tanh={tanh}")
+
+
+def test_norm_kernels_match_float64():
+    from pcompanion_b200 import ops
+    g = torch.Generator(device=dev()).manual_seed(5)
+    m, n = 30_001, 256
+    wide = torch.randn(m, 384, generator=g, device=dev()) * 2 + 0.7
+    x = wide[:, 64:320]                                               # strided view
+    sums = ops.col_stats(x)
+    assert sums.dtype == torch.float64
+    np.testing.assert_allclose(sums[0].cpu().numpy(), x.double().sum(0).cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(sums[1].cpu().numpy(), (x.double() ** 2).sum(0).cpu().numpy(), rtol=1e-12)
+    assert torch.equal(ops.col_stats(x), sums)                        # fixed order
+    scale = torch.rand(n, generator=g, device=dev()) + 0.5
+    shift = torch.randn(n, generator=g, device=dev())
+    y = ops.scale_shift_tanh(x, scale, shift)
+    close(y, torch.tanh(x.double() * scale.double() + shift.double()).cpu().numpy(), what="bn+tanh")
+    y2 = ops.scale_shift_tanh(x, scale, shift, tanh=False)
+    close(y2, (x.double() * scale.double() + shift.double()).cpu().numpy(), what="scale+shift")
+    dy = torch.randn(m, n, generator=g, device=dev())
+    mean, rstd = x.mean(0), 1.0 / x.std(0)
+    s2 = ops.bn_bwd_reduce(dy, x, mean, rstd)
+    xhat = ((x - mean) * rstd).double()
+    np.testing.assert_allclose(s2[0].cpu().numpy(), dy.double().sum(0).cpu().numpy(), rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(s2[1].cpu().numpy(), (dy.double() * xhat).sum(0).cpu().numpy(), rtol=1e-10, atol=1e-9)
+    ca, cb, cc = (torch.randn(n, generator=g, device=dev()) for _ in range(3))
+    close(ops.affine2(dy, x, ca, cb, cc), (ca.double() * dy.double() + cb.double() * x.double() + cc.double()).cpu().numpy(), what="affine2")
+    rowptr = torch.cumsum(torch.tensor([0] + [i % 4 for i in range(m)], device=dev()), 0)
+    g128 = torch.randn(m, 128, generator=g, device=dev())
+    kept, rest = ops.mask_split(g128, rowptr)
+    has = (torch.arange(m, device=dev()) % 4 != 0).unsqueeze(1)
+    assert torch.equal(kept, torch.where(has, g128, torch.zeros_like(g128))) and torch.equal(kept + rest, g128)

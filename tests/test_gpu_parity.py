@@ -511,3 +511,46 @@ def test_full_size_c2_properties():
     lhs = kvt.grad[:, 128:].double().sum(0)
     rhs = d_o[has].double().sum(0)
     assert torch.allclose(lhs, rhs, rtol=1e-6, atol=1e-3 * math.sqrt(n))
+
+
+def test_fused_graph_layer_equals_unfused_path_and_single_rank_partition():
+    """fused.py (one autograd node) vs the op-by-op path, train and eval, plus the world-size-1 halo plan."""
+    from pcompanion_b200 import ops
+    from pcompanion_b200.distributed import HaloPlan, forward_graph_partitioned
+    from pcompanion_b200.fused import p2v_graph_layer
+    g, m = load_p2v("p2v_module.npz")
+    rng = np.random.default_rng(21)
+    n = 700
+    rowptr, col = random_csr(n, n, 8, rng)
+    graph = ops.CSRGraph(torch.tensor(rowptr, device=dev()), torch.tensor(col, device=dev()), n, n)
+    x = torch.randn(n, 128, device=dev())
+    w = torch.randn(n, 128, device=dev())
+    bn = m.ffn[1]
+    saved = (bn.running_mean.clone(), bn.running_var.clone(), bn.num_batches_tracked.clone())
+
+    def run(fn, train):
+        bn.running_mean.copy_(saved[0]); bn.running_var.copy_(saved[1]); bn.num_batches_tracked.copy_(saved[2])
+        m.train(train)
+        m.zero_grad()
+        xt = x.clone().requires_grad_(True)
+        out = fn(xt)
+        (out * w).sum().backward()
+        return out.detach(), xt.grad, [p.grad.clone() for p in m.parameters()], bn.running_mean.clone(), bn.running_var.clone()
+
+    def unfused(xt):
+        h = m._ffn_rows(xt)
+        out = m._attend(h, h, graph)
+        return torch.where((graph.rowptr[1:] > graph.rowptr[:-1]).unsqueeze(1), out, h)
+
+    plan = HaloPlan(graph.rowptr, graph.col, [0, n], 0)
+    for train in (True, False):
+        ref = run(unfused, train)
+        for name, fn in (("fused", lambda xt: p2v_graph_layer(m, xt, graph)),
+                         ("partitioned", lambda xt: forward_graph_partitioned(m, xt, plan))):
+            got = run(fn, train)
+            close(got[0], ref[0].double().cpu().numpy(), what=f"{name} out train={train}")
+            close(got[1], ref[1].double().cpu().numpy(), rel=5e-5, what=f"{name} dx train={train}")
+            for (k, _), a, r in zip(m.named_parameters(), got[2], ref[2]):
+                close(a, r.double().cpu().numpy(), rel=5e-5, atol=3e-6 if k == "ffn.0.bias" else 1e-7, what=f"{name} grad {k} train={train}")
+            close(got[3], ref[3].double().cpu().numpy(), what="running_mean")
+            close(got[4], ref[4].double().cpu().numpy(), what="running_var")
