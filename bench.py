@@ -175,6 +175,8 @@ def run_ours(args):
             ms = sum(per_kernel[name]) / len(per_kernel[name])
             gbs = (be * e + bn * n) / (ms * 1e-3) / 1e9
             kernels[name] = {"ms": round(ms, 4), "algo_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    abi_ms = {name: round(sum(v) / args.steps, 4) for name, v in sorted(per_kernel.items(), key=lambda kv: -sum(kv[1]))}
+    abi_calls = {name: len(v) // args.steps for name, v in per_kernel.items()}
     sparse_ms = sum(k["ms"] for k in kernels.values())
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algo_gbs"], "peak": peak, "unit": "GB/s",
@@ -182,7 +184,9 @@ def run_ours(args):
                 "sparse_fwd_bwd": {"ms": round(sparse_ms, 4),
                                    "algo_gbs": round((3152 * e + 3676 * n) / (sparse_ms * 1e-3) / 1e9, 1),
                                    "frac": round((3152 * e + 3676 * n) / (sparse_ms * 1e-3) / 1e9 / peak, 4)},
-                "kernels": kernels}
+                "kernels": kernels,
+                "abi_ms_per_step": abi_ms, "abi_calls_per_step": abi_calls,
+                "abi_total_ms_per_step": round(sum(abi_ms.values()), 3)}
 
     # ---- end-to-end leg: host buffers, H2D + D2H inside the timed region
     for _ in range(2):

@@ -167,17 +167,20 @@ int pc_hinge_type_bwd(const float* sims, const int64_t* pos, const int64_t* neg,
 /* ------------------------------------------------------------------ (4) retrieval
  * Replaces torch.matmul + torch.topk of p_companion.py:60-64, metrics.py:21,89 and the
  * per-type filter -> matmul -> topk loop of inference.py:93-113.
- * score[r,p] = sum_d double(q[r,d]) * double(c[p,d]) in the fixed "lane-blocked tree" order
- * documented in oracle/retrieval.py; ranking = (score desc, index asc); padding = (-inf, -1).
+ * score[r,p] = sum_d double(q[r,d]) * double(c[p,d]) accumulated sequentially over d in float64 (the
+ * products of float32 values are exact in float64, so the value is fully defined; oracle/retrieval.py
+ * mirrors it); ranking = (score desc, index asc); padding = (-inf, -1).
  *
- * pc_topk_segments: every row scores the contiguous run members[seg_begin[r] .. seg_end[r])
- * of catalog row ids (a type-sorted permutation from pc_sort_keys; or members == NULL for the
- * identity, i.e. a plain slice of the catalog).  k <= 32, dim % 128 == 0. */
-size_t pc_topk_segments_workspace_bytes(int64_t rows, int k, int splits);
-int pc_topk_segments(const float* q, int64_t rows, int dim, const float* catalog, const int32_t* members,
-                     const int64_t* seg_begin, const int64_t* seg_end, int k, int splits, int64_t index_base,
-                     double* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
-                     pc_stream_t stream);
+ * pc_topk_groups: score rows are processed in groups of at most 8 that rank the same contiguous run
+ * members[seg_begin[g] .. seg_end[g]) of catalog row ids (the members of one complementary type in a
+ * type-sorted permutation from pc_sort_keys; members == NULL means the identity, i.e. a slice of the
+ * catalog).  Group g holds the rows row_ids[grp_begin[g] .. grp_begin[g+1]).  A catalog row is read
+ * once per group.  k <= 32, dim % 32 == 0.  Results land at the original row positions. */
+size_t pc_topk_groups_workspace_bytes(int64_t rows, int k, int splits);
+int pc_topk_groups(const float* q, int64_t rows, int dim, const float* catalog, const int32_t* members,
+                   const int32_t* row_ids, const int32_t* grp_begin, const int64_t* seg_begin, const int64_t* seg_end,
+                   int64_t n_groups, int k, int splits, int64_t index_base, double* out_scores, int64_t* out_idx,
+                   void* workspace, size_t workspace_bytes, pc_stream_t stream);
 /* Row-wise top-k of a materialised fp32 matrix [rows, cols] (torch.topk of p_companion.py:64 and
  * metrics.py:21), same ranking rule; scores are returned as exact doubles of the inputs. */
 size_t pc_topk_rows_workspace_bytes(int64_t rows, int k, int splits);

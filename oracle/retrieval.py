@@ -7,8 +7,7 @@ generalised to one masked top-K over the whole catalog as BASELINE.json's north_
 
 Score definition (shared with the CUDA path so indices can be compared bit-exactly):
     score[r, p] = sum_d double(q[r, d]) * double(c[p, d])
-accumulated in float64 in the fixed order given in scores_fp64 (the order a warp of the CUDA
-kernel uses).  Each product of two float32 values is exact in float64, so a fused
+accumulated in float64 sequentially over d = 0 .. D-1 (the order a thread of the CUDA kernel uses).  Each product of two float32 values is exact in float64, so a fused
 multiply-add and a separate multiply/add round identically; only the summation order matters
 and it is fixed.  Ranking: descending score, ties -> lowest catalog index (a stable sort);
 rows with fewer than k eligible products are padded with index -1 / score -inf.
@@ -21,20 +20,14 @@ import numpy as np
 
 
 def scores_fp64(q: np.ndarray, catalog: np.ndarray) -> np.ndarray:
-    """[R, D] x [P, D] -> [R, P] float64 in the fixed order (D % 128 == 0):
-    lane l in 0..31 accumulates dims 128c + 4l + t (c ascending, t = 0..3) sequentially, then the
-    32 lane sums are combined pairwise at distance 16, 8, 4, 2, 1 (a butterfly)."""
-    r, d = q.shape
-    assert d % 128 == 0, "retrieval score order is defined for D % 128 == 0"
-    q64 = q.astype(np.float64).reshape(r, d // 128, 32, 4)
-    c64 = catalog.astype(np.float64).reshape(catalog.shape[0], d // 128, 32, 4)
-    lanes = np.zeros((r, catalog.shape[0], 32), dtype=np.float64)
-    for c in range(d // 128):
-        for t in range(4):
-            lanes += q64[:, None, c, :, t] * c64[None, :, c, :, t]
-    for half in (16, 8, 4, 2, 1):
-        lanes = lanes[..., :half] + lanes[..., half:2 * half]
-    return lanes[..., 0]
+    """[R, D] x [P, D] -> [R, P] float64, accumulated sequentially over d = 0 .. D-1 (the order one
+    thread of the CUDA kernel uses for one (row, product) pair)."""
+    q64 = q.astype(np.float64)
+    c64 = catalog.astype(np.float64)
+    acc = np.zeros((q.shape[0], catalog.shape[0]), dtype=np.float64)
+    for d in range(q.shape[1]):
+        acc += q64[:, d:d + 1] * c64[None, :, d]
+    return acc
 
 
 def masked_topk(q: np.ndarray, catalog: np.ndarray, k: int,

@@ -7,10 +7,11 @@
 // slice of the catalog), which is exactly what the reference's per-type filter computes - the
 // masked-out 99.9 % of a dense [R, P] score matrix is never formed.
 //
-// Scores are float64 sums of exact float32 x float32 products in a fixed order (lane l of a
-// warp owns dims 128c + 4l .. 4l+3 sequentially, then a butterfly over lanes at distance
-// 16, 8, 4, 2, 1), mirrored by oracle/retrieval.py, so indices match the oracle bit for bit;
-// ties rank the lower catalog index first.
+// Scores are float64 sums of exact float32 x float32 products accumulated sequentially over
+// d = 0 .. D-1 (one thread owns one (row, product) pair), mirrored by oracle/retrieval.py, so
+// indices and scores match the oracle bit for bit; ties rank the lower catalog index first.
+// Score rows that rank the same segment (same complementary type) are processed together, eight
+// at a time, so a catalog row is fetched once per group instead of once per score row.
 #include <math.h>
 
 #include "common.cuh"
@@ -53,80 +54,136 @@ __device__ __forceinline__ void warp_topk_insert(Cand& mine, int k, double s, in
   }
 }
 
-// 32 per-lane partial sums (v[j] = this lane's share of product j) -> lane j holds the full sum of
-// product j, combining lanes at distance 16, then 8, 4, 2, 1.
-__device__ __forceinline__ double transpose_reduce(double (&v)[32]) {
-  const int lane = lane_id();
-#pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-    const bool upper = (lane & half) != 0;
-#pragma unroll
-    for (int j = 0; j < half; ++j) {
-      const double keep = upper ? v[j + half] : v[j];
-      const double send = upper ? v[j] : v[j + half];
-      v[j] = keep + __shfl_xor_sync(FULL, send, half);
-    }
-  }
-  return v[0];
-}
+constexpr int RB = 8;            // score rows per group
+constexpr int DCH = 32;          // dims per staged chunk
+constexpr int TILE_LD = 36;      // floats per staged product chunk (32 + 4 pad: conflict-free LDS.128)
 
-// grid = (splits, rows).  CTA (split, r) ranks its share of row r's segment; warp lists are merged
-// by warp 0 and written to part[(r * splits + split) * k ..].
-template <bool PRECOMP>
+// grid = (splits, n_groups).  Group g = score rows row_ids[grp_begin[g] .. grp_begin[g+1]) (<= RB), all ranking
+// members[seg_begin[g] .. seg_end[g]).  Lane = one product of a 32-product batch; chunks of 32 dims are staged
+// through shared memory with coalesced loads, then every lane runs RB sequential fp64 dot products.
 __global__ void __launch_bounds__(TK_WARPS * 32)
-topk_segments_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
-                     const int32_t* __restrict__ members, const int64_t* __restrict__ seg_begin,
-                     const int64_t* __restrict__ seg_end, int k, int splits, int64_t index_base,
-                     double* __restrict__ part_s, int64_t* __restrict__ part_i) {
-  extern __shared__ double q_s[];  // dim doubles (unused when PRECOMP), then TK_WARPS * 32 candidates
-  Cand* lists = reinterpret_cast<Cand*>(q_s + (PRECOMP ? 0 : dim));
+topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
+                   const int32_t* __restrict__ members, const int32_t* __restrict__ row_ids,
+                   const int32_t* __restrict__ grp_begin, const int64_t* __restrict__ seg_begin,
+                   const int64_t* __restrict__ seg_end, int k, int splits, int64_t index_base,
+                   double* __restrict__ part_s, int64_t* __restrict__ part_i) {
+  extern __shared__ double smem_d[];
+  double* q_s = smem_d;                                              // [RB][dim]
+  float* tiles = reinterpret_cast<float*>(q_s + RB * dim);           // [TK_WARPS][32][TILE_LD]
+  Cand* lists = reinterpret_cast<Cand*>(tiles + TK_WARPS * 32 * TILE_LD);   // [TK_WARPS][RB][32]
   const int lane = lane_id(), w = warp_id();
-  const int64_t r = blockIdx.y;
-  const int split = blockIdx.x;
-  if (!PRECOMP) {
-    for (int d = threadIdx.x; d < dim; d += blockDim.x) q_s[d] = double(Q[r * dim + d]);
-    __syncthreads();
+  const int g = blockIdx.y, split = blockIdx.x;
+  const int r_beg = grp_begin[g], n_rows = grp_begin[g + 1] - r_beg;
+  for (int i = threadIdx.x; i < RB * dim; i += blockDim.x) {
+    const int r = i / dim, d = i - r * dim;
+    q_s[i] = r < n_rows ? double(Q[int64_t(row_ids[r_beg + r]) * dim + d]) : 0.0;
   }
-  // PRECOMP: Q is a materialised [rows, dim] fp32 score matrix and every row ranks columns [0, dim)
-  const int64_t beg = PRECOMP ? 0 : seg_begin[r], end = PRECOMP ? int64_t(dim) : seg_end[r];
+  __syncthreads();
+  const int64_t beg = seg_begin[g], end = seg_end[g];
   const int64_t len = end > beg ? end - beg : 0;
   const int64_t per = (ceil_div(len, int64_t(splits)) + 31) / 32 * 32;
   const int64_t sb = beg + per * split;
   const int64_t se = min(end, sb + per);
-  Cand mine{-INFINITY, -1};
-  const int chunks = dim / 128;
-  for (int64_t g = sb + int64_t(w) * 32; g < se; g += TK_WARPS * 32) {
-    const int64_t my_pos = g + lane;
+  Cand mine[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) mine[r] = Cand{-INFINITY, -1};
+  float* tile = tiles + w * 32 * TILE_LD;
+  for (int64_t base = sb + int64_t(w) * 32; base < se; base += TK_WARPS * 32) {
+    const int64_t my_pos = base + lane;
     int64_t my_member = -1;
     if (my_pos < se) my_member = members ? int64_t(members[my_pos]) : my_pos;
-    double score;
-    if (PRECOMP) {
-      score = my_member >= 0 ? double(__ldg(Q + r * dim + my_member)) : 0.0;
-    } else {
-    double v[32];
+    double acc[RB];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int64_t m = __shfl_sync(FULL, (long long)my_member, j);
-      double acc = 0.0;
-      if (m >= 0) {
-        const float4* rowp = reinterpret_cast<const float4*>(catalog + m * dim) + lane;
-        for (int c = 0; c < chunks; ++c) {
-          const float4 x = ld_stream4(rowp + c * 32);
-          const double* qq = q_s + c * 128 + lane * 4;
-          acc = fma(qq[0], double(x.x), acc);
-          acc = fma(qq[1], double(x.y), acc);
-          acc = fma(qq[2], double(x.z), acc);
-          acc = fma(qq[3], double(x.w), acc);
+    for (int r = 0; r < RB; ++r) acc[r] = 0.0;
+    for (int d0 = 0; d0 < dim; d0 += DCH) {
+      // coalesced staging: 8 lanes cover the 128-byte chunk of one product, 4 products per instruction
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int prod = j * 4 + (lane >> 3);
+        const int64_t m = __shfl_sync(FULL, (long long)my_member, prod);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m >= 0) v = ld_stream4(reinterpret_cast<const float4*>(catalog + m * dim + d0) + (lane & 7));
+        *reinterpret_cast<float4*>(tile + prod * TILE_LD + (lane & 7) * 4) = v;
+      }
+      __syncwarp();
+      float c[DCH];
+#pragma unroll
+      for (int j = 0; j < DCH / 4; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + lane * TILE_LD + j * 4);
+        c[4 * j] = v.x; c[4 * j + 1] = v.y; c[4 * j + 2] = v.z; c[4 * j + 3] = v.w;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (r < n_rows) {
+          const double* qq = q_s + r * dim + d0;
+          double a = acc[r];
+#pragma unroll
+          for (int dd = 0; dd < DCH; dd += 2) {
+            const double2 q2 = *reinterpret_cast<const double2*>(qq + dd);
+            a = fma(q2.x, double(c[dd]), a);
+            a = fma(q2.y, double(c[dd + 1]), a);
+          }
+          acc[r] = a;
         }
       }
-      v[j] = acc;
-    }
-    score = transpose_reduce(v);
     }
     const int64_t gidx = my_member >= 0 ? my_member + index_base : -1;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (r < n_rows) {
+        const double thr_s = shfl_d(mine[r].s, k - 1);
+        const int64_t thr_i = shfl_i64(mine[r].i, k - 1);
+        uint32_t cand = __ballot_sync(FULL, gidx >= 0 && ranks_before(acc[r], gidx, thr_s, thr_i));
+        while (cand) {
+          const int src = __ffs(cand) - 1;
+          cand &= cand - 1;
+          warp_topk_insert(mine[r], k, shfl_d(acc[r], src), shfl_i64(gidx, src));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) lists[(w * RB + r) * 32 + lane] = mine[r];
+  __syncthreads();
+  // warp r merges the TK_WARPS lists of row r
+  if (w < n_rows) {
+    Cand best = lists[(0 * RB + w) * 32 + lane];
+    for (int ww = 1; ww < TK_WARPS; ++ww) {
+      for (int j = 0; j < k; ++j) {
+        const Cand c = lists[(ww * RB + w) * 32 + j];
+        if (c.i < 0) break;
+        warp_topk_insert(best, k, c.s, c.i);
+      }
+    }
+    if (lane < k) {
+      const int64_t o = (int64_t(row_ids[r_beg + w]) * splits + split) * k + lane;
+      part_s[o] = best.s;
+      part_i[o] = best.i;
+    }
+  }
+}
+
+// row-wise top-k of a materialised fp32 matrix: grid = (splits, rows)
+__global__ void __launch_bounds__(TK_WARPS * 32)
+topk_values_kernel(const float* __restrict__ V, int64_t cols, int k, int splits, double* __restrict__ part_s,
+                   int64_t* __restrict__ part_i) {
+  __shared__ Cand lists[TK_WARPS * 32];
+  const int lane = lane_id(), w = warp_id();
+  const int64_t r = blockIdx.y;
+  const int split = blockIdx.x;
+  const int64_t per = (ceil_div(cols, int64_t(splits)) + 31) / 32 * 32;
+  const int64_t sb = per * split;
+  const int64_t se = min(cols, sb + per);
+  Cand mine{-INFINITY, -1};
+  for (int64_t base = sb + int64_t(w) * 32; base < se; base += TK_WARPS * 32) {
+    const int64_t c = base + lane;
+    const bool valid = c < se;
+    const double score = valid ? double(__ldg(V + r * cols + c)) : 0.0;
+    const int64_t gidx = valid ? c : -1;
     const double thr_s = shfl_d(mine.s, k - 1);
     const int64_t thr_i = shfl_i64(mine.i, k - 1);
-    uint32_t cand = __ballot_sync(FULL, gidx >= 0 && ranks_before(score, gidx, thr_s, thr_i));
+    uint32_t cand = __ballot_sync(FULL, valid && ranks_before(score, gidx, thr_s, thr_i));
     while (cand) {
       const int src = __ffs(cand) - 1;
       cand &= cand - 1;
@@ -139,7 +196,7 @@ topk_segments_kernel(const float* __restrict__ Q, int dim, const float* __restri
     for (int ww = 1; ww < TK_WARPS; ++ww) {
       for (int j = 0; j < k; ++j) {
         const Cand c = lists[ww * 32 + j];
-        if (c.i < 0) break;  // lists are sorted: the rest is empty
+        if (c.i < 0) break;
         warp_topk_insert(mine, k, c.s, c.i);
       }
     }
@@ -186,38 +243,45 @@ topk_merge_kernel(const double* __restrict__ S, const int64_t* __restrict__ I, i
 
 using namespace pc;
 
-extern "C" size_t pc_topk_segments_workspace_bytes(int64_t rows, int k, int splits) {
+extern "C" size_t pc_topk_groups_workspace_bytes(int64_t rows, int k, int splits) {
   if (rows <= 0 || k <= 0 || splits <= 1) return 0;
   return size_t(rows) * size_t(splits) * size_t(k) * (sizeof(double) + sizeof(int64_t));
 }
 
-extern "C" int pc_topk_segments(const float* q, int64_t rows, int dim, const float* catalog, const int32_t* members,
-                                const int64_t* seg_begin, const int64_t* seg_end, int k, int splits,
-                                int64_t index_base, double* out_scores, int64_t* out_idx, void* workspace,
-                                size_t workspace_bytes, pc_stream_t stream) {
-  PC_REQUIRE(rows >= 0, PC_ERR_INVALID, "topk_segments: negative rows");
-  if (rows == 0) return PC_OK;
-  PC_REQUIRE(q && catalog && seg_begin && seg_end && out_scores && out_idx, PC_ERR_INVALID, "topk_segments: null pointer");
-  PC_REQUIRE(k >= 1 && k <= 32, PC_ERR_UNSUPPORTED, "topk_segments: k=%d outside [1,32]", k);
-  PC_REQUIRE(dim >= 128 && dim % 128 == 0 && dim <= 2048, PC_ERR_UNSUPPORTED, "topk_segments: dim=%d must be a multiple of 128 (<= 2048)", dim);
-  PC_REQUIRE(splits >= 1 && splits <= 65535 && rows <= 65535 * int64_t(32768), PC_ERR_UNSUPPORTED, "topk_segments: bad splits/rows");
+extern "C" int pc_topk_groups(const float* q, int64_t rows, int dim, const float* catalog, const int32_t* members,
+                              const int32_t* row_ids, const int32_t* grp_begin, const int64_t* seg_begin,
+                              const int64_t* seg_end, int64_t n_groups, int k, int splits, int64_t index_base,
+                              double* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                              pc_stream_t stream) {
+  PC_REQUIRE(rows >= 0 && n_groups >= 0, PC_ERR_INVALID, "topk_groups: negative size");
+  if (rows == 0 || n_groups == 0) return PC_OK;
+  PC_REQUIRE(q && catalog && row_ids && grp_begin && seg_begin && seg_end && out_scores && out_idx, PC_ERR_INVALID,
+             "topk_groups: null pointer");
+  PC_REQUIRE(k >= 1 && k <= 32, PC_ERR_UNSUPPORTED, "topk_groups: k=%d outside [1,32]", k);
+  PC_REQUIRE(dim >= DCH && dim % DCH == 0 && dim <= 1024, PC_ERR_UNSUPPORTED, "topk_groups: dim=%d must be a multiple of %d (<= 1024)", dim, DCH);
+  PC_REQUIRE(splits >= 1 && splits <= 65535, PC_ERR_UNSUPPORTED, "topk_groups: bad splits");
   cudaStream_t st = as_stream(stream);
-  const size_t smem = size_t(dim) * sizeof(double) + TK_WARPS * 32 * sizeof(Cand);
+  const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 32 * TILE_LD * sizeof(float) +
+                      size_t(TK_WARPS) * RB * 32 * sizeof(Cand);
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA(cudaFuncSetAttribute(topk_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
+  }
+  PC_REQUIRE(smem <= 160 * 1024, PC_ERR_UNSUPPORTED, "topk_groups: shared memory budget exceeded");
   double* ps = out_scores;
   int64_t* pi = out_idx;
   if (splits > 1) {
-    PC_REQUIRE(workspace && workspace_bytes >= pc_topk_segments_workspace_bytes(rows, k, splits), PC_ERR_WORKSPACE,
-               "topk_segments: workspace too small");
+    PC_REQUIRE(workspace && workspace_bytes >= pc_topk_groups_workspace_bytes(rows, k, splits), PC_ERR_WORKSPACE,
+               "topk_groups: workspace too small");
     ps = reinterpret_cast<double*>(workspace);
     pi = reinterpret_cast<int64_t*>(ps + size_t(rows) * splits * k);
   }
-  // gridDim.y is limited to 65535: walk the rows in slabs
-  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
-    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
-    dim3 grid{unsigned(splits), unsigned(nr), 1u};
-    topk_segments_kernel<false><<<grid, TK_WARPS * 32, smem, st>>>(q + r0 * dim, dim, catalog, members, seg_begin + r0,
-                                                            seg_end + r0, k, splits, index_base,
-                                                            ps + r0 * splits * k, pi + r0 * splits * k);
+  for (int64_t g0 = 0; g0 < n_groups; g0 += 65535) {   // gridDim.y limit
+    const int64_t ng = n_groups - g0 < 65535 ? n_groups - g0 : 65535;
+    dim3 grid{unsigned(splits), unsigned(ng), 1u};
+    topk_groups_kernel<<<grid, TK_WARPS * 32, smem, st>>>(q, dim, catalog, members, row_ids, grp_begin + g0, seg_begin + g0,
+                                                          seg_end + g0, k, splits, index_base, ps, pi);
     PC_LAUNCH_CHECK();
   }
   if (splits > 1) return pc_topk_merge(ps, pi, rows, splits, k, out_scores, out_idx, stream);
@@ -237,7 +301,7 @@ extern "C" int pc_topk_merge(const double* scores, const int64_t* idx, int64_t r
 }
 
 extern "C" size_t pc_topk_rows_workspace_bytes(int64_t rows, int k, int splits) {
-  return pc_topk_segments_workspace_bytes(rows, k, splits);
+  return pc_topk_groups_workspace_bytes(rows, k, splits);
 }
 
 extern "C" int pc_topk_rows(const float* values, int64_t rows, int64_t cols, int k, int splits, double* out_scores,
@@ -256,13 +320,11 @@ extern "C" int pc_topk_rows(const float* values, int64_t rows, int64_t cols, int
     ps = reinterpret_cast<double*>(workspace);
     pi = reinterpret_cast<int64_t*>(ps + size_t(rows) * splits * k);
   }
-  const size_t smem = TK_WARPS * 32 * sizeof(Cand);
   for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
     const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
     dim3 grid{unsigned(splits), unsigned(nr), 1u};
-    topk_segments_kernel<true><<<grid, TK_WARPS * 32, smem, st>>>(values + r0 * cols, int(cols), nullptr, nullptr,
-                                                                  nullptr, nullptr, k, splits, 0,
-                                                                  ps + r0 * splits * k, pi + r0 * splits * k);
+    topk_values_kernel<<<grid, TK_WARPS * 32, 0, st>>>(values + r0 * cols, cols, k, splits, ps + r0 * splits * k,
+                                                       pi + r0 * splits * k);
     PC_LAUNCH_CHECK();
   }
   if (splits > 1) return pc_topk_merge(ps, pi, rows, splits, k, out_scores, out_idx, stream);

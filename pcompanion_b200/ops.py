@@ -381,29 +381,50 @@ def type_hinge(sims, pos, neg, margin: float) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- retrieval
-def _auto_splits(rows: int, avg_len: float) -> int:
+TOPK_GROUP_ROWS = 8   # score rows the kernel ranks per pass over a segment (csrc/retrieval.cu RB)
+
+
+def _auto_splits(units: int, avg_len: float) -> int:
     sms = 148
-    if rows >= 2 * sms:
+    if units >= 2 * sms:
         return 1
-    want = max(1, (2 * sms + rows - 1) // max(rows, 1))
+    want = max(1, (2 * sms + units - 1) // max(units, 1))
     cap = max(1, int(avg_len // 256))
     return max(1, min(want, cap, 1024))
 
 
 def topk_segments(q: torch.Tensor, catalog: torch.Tensor, seg_begin: torch.Tensor, seg_end: torch.Tensor, k: int,
                   members: Optional[torch.Tensor] = None, index_base: int = 0, splits: Optional[int] = None):
-    """Exact top-k of every row over its run of catalog rows; returns (scores f64 [R,k], idx i64 [R,k])."""
+    """Exact top-k of every row over its run of catalog rows; returns (scores f64 [R,k], idx i64 [R,k]).
+    Rows that rank the same run (same complementary type) are grouped, eight per pass (pc_topk_groups)."""
     rows, dim = q.shape
+    dev_ = q.device
+    out_s = torch.empty(rows, k, dtype=F64, device=dev_)
+    out_i = torch.empty(rows, k, dtype=I64, device=dev_)
+    if rows == 0:
+        return out_s, out_i
+    # index plumbing on [rows]-sized tensors: order rows by segment, cut runs into groups of <= 8
+    key = seg_begin * (int(seg_end.max().item()) + 1) + seg_end
+    order = torch.argsort(key, stable=True)
+    skey = key[order]
+    ar = torch.arange(rows, device=dev_)
+    change = torch.ones(rows, dtype=torch.bool, device=dev_)
+    change[1:] = skey[1:] != skey[:-1]
+    run_start = torch.cummax(torch.where(change, ar, torch.zeros_like(ar)), 0).values
+    new_group = change | ((ar - run_start) % TOPK_GROUP_ROWS == 0)
+    starts = torch.nonzero(new_group).squeeze(1)
+    n_groups = starts.numel()
+    grp_begin = torch.cat([starts, torch.tensor([rows], device=dev_)]).to(I32).contiguous()
+    g_beg = seg_begin[order][starts].contiguous()
+    g_end = seg_end[order][starts].contiguous()
+    row_ids = order.to(I32).contiguous()
     if splits is None:
-        avg = float((seg_end - seg_begin).float().mean().item()) if rows else 0.0
-        splits = _auto_splits(rows, avg)
-    out_s = torch.empty(rows, k, dtype=F64, device=q.device)
-    out_i = torch.empty(rows, k, dtype=I64, device=q.device)
-    ws = _lib.workspace(_lib.LIB.pc_topk_segments_workspace_bytes(rows, k, splits), q.device)
-    call("pc_topk_segments", dev(q.contiguous(), F32, "q"), rows, dim, dev(catalog, F32, "catalog"),
-         dev(members, I32, "members"), dev(seg_begin, I64, "seg_begin"), dev(seg_end, I64, "seg_end"), k, splits,
-         int(index_base), dev(out_s, F64, "out_scores"), dev(out_i, I64, "out_idx"), dev(ws, torch.uint8, "ws"),
-         ws.numel(), stream())
+        splits = _auto_splits(n_groups, float((g_end - g_beg).float().mean().item()))
+    ws = _lib.workspace(_lib.LIB.pc_topk_groups_workspace_bytes(rows, k, splits), dev_)
+    call("pc_topk_groups", dev(q.contiguous(), F32, "q"), rows, dim, dev(catalog, F32, "catalog"),
+         dev(members, I32, "members"), dev(row_ids, I32, "row_ids"), dev(grp_begin, I32, "grp_begin"),
+         dev(g_beg, I64, "seg_begin"), dev(g_end, I64, "seg_end"), n_groups, k, splits, int(index_base),
+         dev(out_s, F64, "out_scores"), dev(out_i, I64, "out_idx"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
     return out_s, out_i
 
 

@@ -45,8 +45,8 @@ def test_workspace_queries_need_no_gpu():
     assert _lib.LIB.pc_sort_keys_workspace_bytes(0) == 0
     assert _lib.LIB.pc_sort_keys_workspace_bytes(1_000_000) >= 8_000_000
     assert _lib.LIB.pc_compact_workspace_bytes(1_000_000) >= 8_000_000
-    assert _lib.LIB.pc_topk_segments_workspace_bytes(10, 10, 1) == 0
-    assert _lib.LIB.pc_topk_segments_workspace_bytes(10, 10, 4) == 10 * 4 * 10 * 16
+    assert _lib.LIB.pc_topk_groups_workspace_bytes(10, 10, 1) == 0
+    assert _lib.LIB.pc_topk_groups_workspace_bytes(10, 10, 4) == 10 * 4 * 10 * 16
 
 
 def test_argument_errors_are_reported_without_a_gpu():
