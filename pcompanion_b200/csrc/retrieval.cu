@@ -56,7 +56,7 @@ __device__ __forceinline__ void warp_topk_insert(Cand& mine, int k, double s, in
 
 constexpr int RB = 8;            // score rows per group
 constexpr int DCH = 32;          // dims per staged chunk
-constexpr int TILE_LD = 36;      // floats per staged product chunk (32 + 4 pad: conflict-free LDS.128)
+constexpr int TILE_LD = 34;      // doubles per staged product chunk (32 + 2 pad: conflict-free LDS.128 across lanes)
 
 // grid = (splits, n_groups).  Group g = score rows row_ids[grp_begin[g] .. grp_begin[g+1]) (<= RB), all ranking
 // members[seg_begin[g] .. seg_end[g]).  Lane = one product of a 32-product batch; chunks of 32 dims are staged
@@ -69,7 +69,7 @@ topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict
                    double* __restrict__ part_s, int64_t* __restrict__ part_i) {
   extern __shared__ double smem_d[];
   double* q_s = smem_d;                                              // [RB][dim]
-  float* tiles = reinterpret_cast<float*>(q_s + RB * dim);           // [TK_WARPS][32][TILE_LD]
+  double* tiles = q_s + RB * dim;                                    // [TK_WARPS][32][TILE_LD], converted to fp64 once
   Cand* lists = reinterpret_cast<Cand*>(tiles + TK_WARPS * 32 * TILE_LD);   // [TK_WARPS][RB][32]
   const int lane = lane_id(), w = warp_id();
   const int g = blockIdx.y, split = blockIdx.x;
@@ -87,7 +87,7 @@ topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict
   Cand mine[RB];
 #pragma unroll
   for (int r = 0; r < RB; ++r) mine[r] = Cand{-INFINITY, -1};
-  float* tile = tiles + w * 32 * TILE_LD;
+  double* tile = tiles + w * 32 * TILE_LD;
   for (int64_t base = sb + int64_t(w) * 32; base < se; base += TK_WARPS * 32) {
     const int64_t my_pos = base + lane;
     int64_t my_member = -1;
@@ -96,37 +96,43 @@ topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r] = 0.0;
     for (int d0 = 0; d0 < dim; d0 += DCH) {
-      // coalesced staging: 8 lanes cover the 128-byte chunk of one product, 4 products per instruction
+      // coalesced staging: 8 lanes cover the 128-byte chunk of one product, 4 products per instruction;
+      // the float -> double conversion happens here, once per element, not once per (row, element)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int prod = j * 4 + (lane >> 3);
         const int64_t m = __shfl_sync(FULL, (long long)my_member, prod);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m >= 0) v = ld_stream4(reinterpret_cast<const float4*>(catalog + m * dim + d0) + (lane & 7));
-        *reinterpret_cast<float4*>(tile + prod * TILE_LD + (lane & 7) * 4) = v;
-      }
-      __syncwarp();
-      float c[DCH];
-#pragma unroll
-      for (int j = 0; j < DCH / 4; ++j) {
-        const float4 v = *reinterpret_cast<const float4*>(tile + lane * TILE_LD + j * 4);
-        c[4 * j] = v.x; c[4 * j + 1] = v.y; c[4 * j + 2] = v.z; c[4 * j + 3] = v.w;
+        double2* dst = reinterpret_cast<double2*>(tile + prod * TILE_LD + (lane & 7) * 4);
+        dst[0] = make_double2(double(v.x), double(v.y));
+        dst[1] = make_double2(double(v.z), double(v.w));
       }
       __syncwarp();
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        if (r < n_rows) {
-          const double* qq = q_s + r * dim + d0;
-          double a = acc[r];
+      for (int half = 0; half < 2; ++half) {
+        double cd[DCH / 2];
 #pragma unroll
-          for (int dd = 0; dd < DCH; dd += 2) {
-            const double2 q2 = *reinterpret_cast<const double2*>(qq + dd);
-            a = fma(q2.x, double(c[dd]), a);
-            a = fma(q2.y, double(c[dd + 1]), a);
+        for (int j = 0; j < DCH / 4; ++j) {
+          const double2 v = *reinterpret_cast<const double2*>(tile + lane * TILE_LD + half * (DCH / 2) + 2 * j);
+          cd[2 * j] = v.x; cd[2 * j + 1] = v.y;
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (r < n_rows) {
+            const double* qq = q_s + r * dim + d0 + half * (DCH / 2);
+            double a = acc[r];
+#pragma unroll
+            for (int dd = 0; dd < DCH / 2; dd += 2) {
+              const double2 q2 = *reinterpret_cast<const double2*>(qq + dd);
+              a = fma(q2.x, cd[dd], a);
+              a = fma(q2.y, cd[dd + 1], a);
+            }
+            acc[r] = a;
           }
-          acc[r] = a;
         }
       }
+      __syncwarp();
     }
     const int64_t gidx = my_member >= 0 ? my_member + index_base : -1;
 #pragma unroll
@@ -261,7 +267,7 @@ extern "C" int pc_topk_groups(const float* q, int64_t rows, int dim, const float
   PC_REQUIRE(dim >= DCH && dim % DCH == 0 && dim <= 1024, PC_ERR_UNSUPPORTED, "topk_groups: dim=%d must be a multiple of %d (<= 1024)", dim, DCH);
   PC_REQUIRE(splits >= 1 && splits <= 65535, PC_ERR_UNSUPPORTED, "topk_groups: bad splits");
   cudaStream_t st = as_stream(stream);
-  const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 32 * TILE_LD * sizeof(float) +
+  const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 32 * TILE_LD * sizeof(double) +
                       size_t(TK_WARPS) * RB * 32 * sizeof(Cand);
   static bool configured = false;
   if (!configured) {
