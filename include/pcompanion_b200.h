@@ -118,9 +118,10 @@ int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, const int64_t*
  * 2 (. + bias) * (1 - aux^2) (gradient through tanh, aux = tanh output),
  * 3 row r keeps (. + bias) if rowptr[r+1] > rowptr[r] else takes aux[r, :] (product2vec.py:76),
  * 4 (. + bias) + aux. */
+size_t pc_linear_workspace_bytes(int n, int k);   /* holds the weight pre-split into tf32 hi | lo */
 int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, const float* bias,
                      int epilogue, const float* aux, int64_t ld_aux, const int64_t* rowptr, float* out0, int64_t ld0,
-                     int split, float* out1, int64_t ld1, pc_stream_t stream);
+                     int split, float* out1, int64_t ld1, void* workspace, size_t workspace_bytes, pc_stream_t stream);
 
 /* Weight / bias gradient of such a projection (autograd's AddmmBackward for the weight):
  *   dW[n, k] = sum_m dY[m, n] X[m, k],  db[n] = sum_m dY[m, n]  (db may be NULL)

@@ -22,6 +22,7 @@
 //               tanh-gradient / row-select, 128-byte row segments straight to global memory
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -30,15 +31,23 @@ namespace {
 
 constexpr int BM = 128;                 // rows per tile (UMMA M)
 constexpr int BK = 32;                  // fp32 per K block = one 128-byte swizzle row
-constexpr int STAGES = 3;
 constexpr int MAX_BN = 128;             // columns per tile: 2 accumulators x 2 buffers x 128 = the 512 TMEM columns
 constexpr int A_BYTES = BM * BK * 4;    // 16 KB
 constexpr int B_BYTES = MAX_BN * BK * 4;  // 16 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands = 64 KB
+constexpr int A_STAGES = 4;             // activation tiles come from HBM: deep ring (raw tile becomes the hi tile in place)
+constexpr int LO_STAGES = 2;            // lo tiles of A live only between the split and the MMA
+constexpr int B_STAGES = 3;             // weight tiles (pre-split hi | lo) come from L2
+constexpr int OFF_LO = A_STAGES * A_BYTES;
+constexpr int OFF_B = OFF_LO + LO_STAGES * A_BYTES;
+constexpr int OFF_OUT = OFF_B + B_STAGES * 2 * B_BYTES;   // [128 rows x 32 cols] output staging tile for the TMA store
+constexpr int OUT_BYTES = BM * 32 * 4;
+constexpr int OPERAND_BYTES = OFF_OUT + OUT_BYTES;        // 64 + 32 + 96 + 16 = 208 KB
 constexpr int GEMM_THREADS = 512;
 constexpr int SPLIT_THREADS = 256;      // warps 8-15
 constexpr int SMEM_MISC = 4096;         // barriers, tmem pointer, bias
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 + SMEM_MISC;
+constexpr int GEMM_SMEM = OPERAND_BYTES + 1024 + SMEM_MISC;
+constexpr int STAGES = 3;               // (wgrad kernel's ring depth is defined separately below)
+constexpr int STAGE_BYTES = 0;          // unused by the forward kernel
 
 enum Epilogue { EPI_BIAS = 0, EPI_BIAS_TANH = 1, EPI_TANH_GRAD = 2, EPI_BIAS_SELECT = 3, EPI_BIAS_ADD = 4 };
 
@@ -129,35 +138,58 @@ __device__ __forceinline__ uint32_t instr_desc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
 }
 
-struct Pipe {
+template <int N>
+struct Ring {
   int stage = 0;
   uint32_t phase = 0;
   __device__ __forceinline__ void advance() {
-    if (++stage == STAGES) {
+    if (++stage == N) {
       stage = 0;
       phase ^= 1;
     }
   }
 };
 
+// w_hi = rn_tf32(w), w_lo = rn_tf32(w - w_hi): the weight operand is split once per call, not once per tile
+__global__ void split_tf32_kernel(const float4* __restrict__ w, int64_t n4, float4* __restrict__ hi, float4* __restrict__ lo) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = w[i];
+  float4 h, l;
+  h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+  l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+  hi[i] = h;
+  lo[i] = l;
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                     const LinearParams p) {
+linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
+                     const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_out0,
+                     const __grid_constant__ CUtensorMap map_out1, const LinearParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* misc = smem + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);       // full[3], ready[3], empty[3], tmem_full[2], tmem_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-  float* bias_s = reinterpret_cast<float*>(misc + 256);     // up to 768 floats
-  const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + 3), empty_bar = smem_u32(bars + 6);
-  const uint32_t tfull_bar = smem_u32(bars + 9), tempty_bar = smem_u32(bars + 11);
+  uint8_t* misc = smem + OPERAND_BYTES;
+  // barriers: a_full[5] a_ready[5] a_empty[5] lo_empty[2] b_full[3] b_empty[3] tmem_full[2] tmem_empty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint8_t* out_tile = smem + OFF_OUT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
+  float* bias_s = reinterpret_cast<float*>(misc + 512);     // up to 768 floats
+  const uint32_t a_full = smem_u32(bars + 0), a_ready = smem_u32(bars + A_STAGES), a_empty = smem_u32(bars + 2 * A_STAGES);
+  const uint32_t lo_empty = smem_u32(bars + 3 * A_STAGES), b_full = smem_u32(bars + 3 * A_STAGES + LO_STAGES);
+  const uint32_t b_empty = smem_u32(bars + 3 * A_STAGES + LO_STAGES + B_STAGES);
+  const uint32_t tfull_bar = smem_u32(bars + 3 * A_STAGES + LO_STAGES + 2 * B_STAGES), tempty_bar = tfull_bar + 16;
   const int warp = warp_id(), lane = lane_id();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar + 8 * s, 1);
-      mbar_init(ready_bar + 8 * s, SPLIT_THREADS);
-      mbar_init(empty_bar + 8 * s, 1);
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(a_full + 8 * s, 1);
+      mbar_init(a_ready + 8 * s, SPLIT_THREADS);
+      mbar_init(a_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < LO_STAGES; ++s) mbar_init(lo_empty + 8 * s, 1);
+    for (int s = 0; s < B_STAGES; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
@@ -181,24 +213,40 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t b_tile_bytes = uint32_t(p.bn) * BK * 4;
 
   if (warp == 0) {
-    // ---------------- TMA producer
+    // ---------------- TMA producer, activations (HBM)
     if (lane == 0) {
-      Pipe pipe;
+      Ring<A_STAGES> ra;
       for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int m0 = int((t / p.n_tiles) * BM), n0 = int(t % p.n_tiles) * p.bn;
+        const int m0 = int((t / p.n_tiles) * BM);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar + 8 * pipe.stage, pipe.phase ^ 1);
-          uint8_t* st = smem + pipe.stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar + 8 * pipe.stage, A_BYTES + b_tile_bytes);
-          tma_load_2d(smem_u32(st), &map_a, kb * BK, m0, full_bar + 8 * pipe.stage);
-          tma_load_2d(smem_u32(st + 2 * A_BYTES), &map_w, kb * BK, n0, full_bar + 8 * pipe.stage);
-          pipe.advance();
+          mbar_wait(a_empty + 8 * ra.stage, ra.phase ^ 1);
+          mbar_arrive_expect_tx(a_full + 8 * ra.stage, A_BYTES);
+          tma_load_2d(smem_u32(smem + ra.stage * A_BYTES), &map_a, kb * BK, m0, a_full + 8 * ra.stage);
+          ra.advance();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------- TMA producer, pre-split weights (L2)
+    if (lane == 0) {
+      Ring<B_STAGES> rb;
+      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int n0 = int(t % p.n_tiles) * p.bn;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(b_empty + 8 * rb.stage, rb.phase ^ 1);
+          uint8_t* st = smem + OFF_B + rb.stage * 2 * B_BYTES;
+          mbar_arrive_expect_tx(b_full + 8 * rb.stage, 2 * b_tile_bytes);
+          tma_load_2d(smem_u32(st), &map_whi, kb * BK, n0, b_full + 8 * rb.stage);
+          tma_load_2d(smem_u32(st + B_BYTES), &map_wlo, kb * BK, n0, b_full + 8 * rb.stage);
+          rb.advance();
         }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer
-    Pipe pipe;
+    Ring<A_STAGES> ra;
+    Ring<LO_STAGES> rl;
+    Ring<B_STAGES> rb;
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t idesc = instr_desc_tf32(p.bn);
@@ -207,12 +255,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tc_fence_after();
       const uint32_t d_main = tmem_base + uint32_t(acc * 2 * MAX_BN), d_cross = d_main + MAX_BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(ready_bar + 8 * pipe.stage, pipe.phase);
+        mbar_wait(b_full + 8 * rb.stage, rb.phase);
+        mbar_wait(a_ready + 8 * ra.stage, ra.phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t st = smem_u32(smem + pipe.stage * STAGE_BYTES);
-          const uint64_t a_hi = smem_desc_k_sw128(st), a_lo = smem_desc_k_sw128(st + A_BYTES);
-          const uint64_t b_hi = smem_desc_k_sw128(st + 2 * A_BYTES), b_lo = smem_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
+          const uint32_t base = smem_u32(smem);
+          const uint64_t a_hi = smem_desc_k_sw128(base + ra.stage * A_BYTES);
+          const uint64_t a_lo = smem_desc_k_sw128(base + OFF_LO + rl.stage * A_BYTES);
+          const uint64_t b_hi = smem_desc_k_sw128(base + OFF_B + rb.stage * 2 * B_BYTES);
+          const uint64_t b_lo = smem_desc_k_sw128(base + OFF_B + rb.stage * 2 * B_BYTES + B_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t adv = uint64_t(kk * 32 >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle row
@@ -220,11 +271,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
             umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
           }
-          umma_commit(empty_bar + 8 * pipe.stage);
+          umma_commit(a_empty + 8 * ra.stage);
+          umma_commit(lo_empty + 8 * rl.stage);
+          umma_commit(b_empty + 8 * rb.stage);
           if (kb == k_blocks - 1) umma_commit(tfull_bar + 8 * acc);
         }
         __syncwarp();
-        pipe.advance();
+        ra.advance();
+        rl.advance();
+        rb.advance();
       }
       if (++acc == 2) {
         acc = 0;
@@ -232,37 +287,41 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
   } else if (warp >= 8) {
-    // ---------------- operand split: hi = rn_tf32(x) in place, lo = x - hi
-    Pipe pipe;
+    // ---------------- activation split: hi = rn_tf32(x) in place, lo = x - hi into the lo ring
+    Ring<A_STAGES> ra;
+    Ring<LO_STAGES> rl;
     const int tid = threadIdx.x - 256;
-    const int a_vec = A_BYTES / 16, b_vec = int(b_tile_bytes / 16);
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(full_bar + 8 * pipe.stage, pipe.phase);
-        uint8_t* st = smem + pipe.stage * STAGE_BYTES;
-#pragma unroll 4
-        for (int i = tid; i < a_vec + b_vec; i += SPLIT_THREADS) {
-          uint8_t* hi_p = i < a_vec ? st + i * 16 : st + 2 * A_BYTES + (i - a_vec) * 16;
-          uint8_t* lo_p = hi_p + (i < a_vec ? A_BYTES : B_BYTES);
-          const float4 v = *reinterpret_cast<const float4*>(hi_p);
+        mbar_wait(a_full + 8 * ra.stage, ra.phase);
+        mbar_wait(lo_empty + 8 * rl.stage, rl.phase ^ 1);
+        uint8_t* hi_base = smem + ra.stage * A_BYTES;
+        uint8_t* lo_base = smem + OFF_LO + rl.stage * A_BYTES;
+#pragma unroll
+        for (int i = tid; i < A_BYTES / 16; i += SPLIT_THREADS) {
+          const float4 v = *reinterpret_cast<const float4*>(hi_base + i * 16);
           float4 h, l;
           h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
           l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-          *reinterpret_cast<float4*>(hi_p) = h;
-          *reinterpret_cast<float4*>(lo_p) = l;
+          *reinterpret_cast<float4*>(hi_base + i * 16) = h;
+          *reinterpret_cast<float4*>(lo_base + i * 16) = l;
         }
         fence_proxy_async();
-        mbar_arrive(ready_bar + 8 * pipe.stage);
-        pipe.advance();
+        mbar_arrive(a_ready + 8 * ra.stage);
+        ra.advance();
+        rl.advance();
       }
     }
   } else if (warp >= 4) {
-    // ---------------- epilogue
+    // ---------------- epilogue: TMEM -> registers -> (bias / activation) -> swizzled smem tile -> TMA store
     int acc = 0;
     uint32_t acc_phase = 0;
     const int quad = warp - 4;
+    const int trow = quad * 32 + lane;                      // row of the tile this thread owns
+    const bool issuer = threadIdx.x == 128;                 // first epilogue thread issues the bulk stores
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int64_t row = (t / p.n_tiles) * BM + quad * 32 + lane;
+      const int m0 = int((t / p.n_tiles) * BM);
+      const int64_t row = int64_t(m0) + trow;
       const int n0 = int(t % p.n_tiles) * p.bn;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
@@ -272,29 +331,44 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         uint32_t r[32], rc[32];
         tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + c0), r);
         tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + MAX_BN + c0), rc);
+        const int n = n0 + c0;
+        float y[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
-        if (row < p.m) {
-          const int n = n0 + c0;
-          float* dst = n < p.split ? p.out0 + row * p.ld0 + n : p.out1 + row * p.ld1 + (n - p.split);
-          const float* aux = p.aux ? p.aux + row * p.ld_aux + n : nullptr;
+        for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]) + bias_s[n + j];
+        if (p.epilogue == EPI_BIAS_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = tanhf(y[j]);
+        } else if (p.epilogue != EPI_BIAS && row < p.m) {
+          const float* aux = p.aux + row * p.ld_aux + n;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 y = make_float4(__uint_as_float(r[j]) + bias_s[n + j], __uint_as_float(r[j + 1]) + bias_s[n + j + 1],
-                                   __uint_as_float(r[j + 2]) + bias_s[n + j + 2], __uint_as_float(r[j + 3]) + bias_s[n + j + 3]);
-            if (p.epilogue == EPI_BIAS_TANH) {
-              y = make_float4(tanhf(y.x), tanhf(y.y), tanhf(y.z), tanhf(y.w));
-            } else if (p.epilogue == EPI_TANH_GRAD) {
-              const float4 a = *reinterpret_cast<const float4*>(aux + j);
-              y = make_float4(y.x * (1.f - a.x * a.x), y.y * (1.f - a.y * a.y), y.z * (1.f - a.z * a.z), y.w * (1.f - a.w * a.w));
-            } else if (p.epilogue == EPI_BIAS_SELECT) {
-              if (!keep) y = *reinterpret_cast<const float4*>(aux + j);
+            const float4 a = *reinterpret_cast<const float4*>(aux + j);
+            if (p.epilogue == EPI_TANH_GRAD) {
+              y[j] *= 1.f - a.x * a.x; y[j + 1] *= 1.f - a.y * a.y; y[j + 2] *= 1.f - a.z * a.z; y[j + 3] *= 1.f - a.w * a.w;
             } else if (p.epilogue == EPI_BIAS_ADD) {
-              const float4 a = *reinterpret_cast<const float4*>(aux + j);
-              y = make_float4(y.x + a.x, y.y + a.y, y.z + a.z, y.w + a.w);
+              y[j] += a.x; y[j + 1] += a.y; y[j + 2] += a.z; y[j + 3] += a.w;
+            } else if (!keep) {  // EPI_BIAS_SELECT
+              y[j] = a.x; y[j + 1] = a.y; y[j + 2] = a.z; y[j + 3] = a.w;
             }
-            *reinterpret_cast<float4*>(dst + j) = y;
           }
+        }
+        // the previous chunk's bulk store must have finished reading the staging tile
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j)   // 128-byte swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+          *reinterpret_cast<float4*>(out_tile + trow * 128 + ((j ^ (trow & 7)) << 4)) =
+              make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          const bool first = n < p.split;
+          const CUtensorMap* map = first ? &map_out0 : &map_out1;
+          const int cn = first ? n : n - p.split;
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(cn),
+                       "r"(m0), "r"(smem_u32(out_tile))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
@@ -304,6 +378,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         acc_phase ^= 1;
       }
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -556,7 +631,8 @@ EncodeTiledFn encode_tiled() {
 }
 
 // row-major fp32 [rows, cols] -> boxes of [box_rows, 32 cols], 128-byte swizzle, zero fill out of bounds
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+             CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
   EncodeTiledFn fn = encode_tiled();
   PC_REQUIRE(fn, PC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
@@ -564,8 +640,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, in
   cuuint32_t box[2] = {BK, cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PC_REQUIRE(r == CUDA_SUCCESS, PC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] ld %lld", int(r),
              (long long)rows, (long long)cols, (long long)ld);
   return PC_OK;
@@ -576,20 +651,26 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, in
 
 using namespace pc;
 
+extern "C" size_t pc_linear_workspace_bytes(int n, int k) { return align_up(size_t(n) * k * sizeof(float), 256) * 2; }
+
 extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, const float* bias,
                                 int epilogue, const float* aux, int64_t ld_aux, const int64_t* rowptr, float* out0,
-                                int64_t ld0, int split, float* out1, int64_t ld1, pc_stream_t stream) {
+                                int64_t ld0, int split, float* out1, int64_t ld1, void* workspace, size_t workspace_bytes,
+                                pc_stream_t stream) {
   PC_REQUIRE(m >= 0, PC_ERR_INVALID, "linear: negative row count");
   if (m == 0) return PC_OK;
-  PC_REQUIRE(a && w && out0, PC_ERR_INVALID, "linear: null pointer");
+  PC_REQUIRE(a && w && out0 && workspace, PC_ERR_INVALID, "linear: null pointer");
   PC_REQUIRE(k >= BK && k % BK == 0 && k <= 4096, PC_ERR_UNSUPPORTED, "linear: k=%d must be a multiple of %d", k, BK);
   PC_REQUIRE(n >= 32 && n % 32 == 0 && n <= 768, PC_ERR_UNSUPPORTED, "linear: n=%d must be a multiple of 32 in [32, 768]", n);
   PC_REQUIRE(split > 0 && split <= n && split % 32 == 0 && (split == n || out1), PC_ERR_INVALID, "linear: bad output split");
   PC_REQUIRE(lda % 4 == 0 && ld0 % 4 == 0 && (split == n || ld1 % 4 == 0), PC_ERR_INVALID, "linear: leading dimensions must be multiples of 4 floats");
+  PC_REQUIRE((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out0) | reinterpret_cast<uintptr_t>(out1)) % 16 == 0, PC_ERR_INVALID,
+             "linear: A / outputs must be 16-byte aligned (TMA)");
   PC_REQUIRE(epilogue >= EPI_BIAS && epilogue <= EPI_BIAS_ADD, PC_ERR_INVALID, "linear: unknown epilogue %d", epilogue);
   PC_REQUIRE((epilogue != EPI_TANH_GRAD && epilogue != EPI_BIAS_SELECT && epilogue != EPI_BIAS_ADD) || (aux && ld_aux % 4 == 0),
              PC_ERR_INVALID, "linear: epilogue needs aux");
   PC_REQUIRE(epilogue != EPI_BIAS_SELECT || rowptr, PC_ERR_INVALID, "linear: select epilogue needs rowptr");
+  PC_REQUIRE(workspace_bytes >= pc_linear_workspace_bytes(n, k), PC_ERR_WORKSPACE, "linear: workspace too small");
   LinearParams p;
   p.m = m; p.n = n; p.k = k;
   p.n_tiles = (n + MAX_BN - 1) / MAX_BN;
@@ -598,9 +679,28 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   p.bias = bias;
   p.out0 = out0; p.ld0 = int(ld0); p.split = split; p.out1 = out1; p.ld1 = int(ld1);
   p.epilogue = epilogue; p.aux = aux; p.ld_aux = int(ld_aux); p.rowptr = rowptr;
-  CUtensorMap map_a, map_w;
-  if (int rc = make_map(&map_a, a, m, k, lda, BM)) return rc;
-  if (int rc = make_map(&map_w, w, n, k, k, p.bn)) return rc;
+  cudaStream_t st = as_stream(stream);
+  float* w_hi = reinterpret_cast<float*>(workspace);
+  float* w_lo = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(size_t(n) * k * sizeof(float), 256));
+  const int64_t n4 = int64_t(n) * k / 4;
+  split_tf32_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(w), n4,
+                                                               reinterpret_cast<float4*>(w_hi), reinterpret_cast<float4*>(w_lo));
+  PC_LAUNCH_CHECK();
+  CUtensorMap map_a, map_whi, map_wlo;
+  // consecutive K blocks of a row are adjacent in memory: let L2 fetch 256 B per miss so the next block's
+  // request hits, halving the DRAM page activations of the strided [128 x 32] activation boxes
+  static const int promo_env = getenv("PC_GEMM_L2PROMO") ? atoi(getenv("PC_GEMM_L2PROMO")) : 256;
+  const CUtensorMapL2promotion promo = promo_env == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo_env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (int rc = make_map(&map_a, a, m, k, lda, BM, promo)) return rc;
+  if (int rc = make_map(&map_whi, w_hi, n, k, k, p.bn)) return rc;
+  if (int rc = make_map(&map_wlo, w_lo, n, k, k, p.bn)) return rc;
+  CUtensorMap map_out0, map_out1;
+  if (int rc = make_map(&map_out0, out0, m, split, ld0, BM)) return rc;
+  if (split < n) {
+    if (int rc = make_map(&map_out1, out1, m, n - split, ld1, BM)) return rc;
+  } else {
+    map_out1 = map_out0;
+  }
   static bool configured = false;
   if (!configured) {
     PC_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
@@ -608,7 +708,7 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   }
   const int64_t tiles = ((m + BM - 1) / BM) * p.n_tiles;
   const int grid = int(tiles < sm_count() ? tiles : sm_count());
-  linear_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, as_stream(stream)>>>(map_a, map_w, p);
+  linear_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out0, map_out1, p);
   PC_LAUNCH_CHECK();
   return PC_OK;
 }

@@ -233,10 +233,12 @@ def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
         out0 = torch.empty(m, split_, dtype=F32, device=a.device)
     if out1 is None and split_ < n:
         out1 = torch.empty(m, n - split_, dtype=F32, device=a.device)
+    ws = _lib.workspace(_lib.LIB.pc_linear_workspace_bytes(n, k), a.device)
     call("pc_linear_tf32x3", _f32_cuda(a, "a"), m, k, a.stride(0), dev(w, F32, "w"), n, dev(bias, F32, "bias"), epilogue,
          _f32_cuda(aux, "aux") if aux is not None else None, aux.stride(0) if aux is not None else 0,
          dev(rowptr, I64, "rowptr"), _f32_cuda(out0, "out0"), out0.stride(0), split_,
-         _f32_cuda(out1, "out1") if out1 is not None else None, out1.stride(0) if out1 is not None else 0, stream())
+         _f32_cuda(out1, "out1") if out1 is not None else None, out1.stride(0) if out1 is not None else 0,
+         dev(ws, torch.uint8, "ws"), ws.numel(), stream())
     return out0 if out1 is None else (out0, out1)
 
 
