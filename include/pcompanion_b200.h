@@ -102,6 +102,9 @@ int pc_gat_fwd(const float* q, int64_t ld_q, const float* kv, const int64_t* row
 int pc_gat_bwd_dst(const float* q, int64_t ld_q, const float* kv, const int64_t* rowptr, const int32_t* col,
                    int64_t n_dst, int heads, float dropout_p, uint64_t seed, const float* o, const float* d_o,
                    int64_t ld_do, float* stats, float* dq, int64_t ld_dq, pc_stream_t stream);
+/* stats[:,1,:] = dO . O per head on its own (pc_gat_bwd_dst also writes it); lets the src-major pass run
+ * first so the multi-GPU path can start returning halo gradients while the dst-major pass computes. */
+int pc_gat_delta(const float* o, const float* d_o, int64_t ld_do, int64_t n, int heads, float* stats, pc_stream_t stream);
 /* src-major backward over the CSC (colptr [n_src+1], row [E] = dst ids per src, ascending):
  * dkv [n_src, 256]. */
 int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, const int64_t* colptr, const int32_t* row,

@@ -205,6 +205,19 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
   dKV[j * lddkv4 + ROW4 + lane] = dv;
 }
 
+// stats[i, 1, h] = dO_i . O_i per head (the softmax-gradient row constant); lets the src-major backward run
+// before the dst-major one (the multi-GPU path starts its reverse halo exchange as early as possible)
+template <int H>
+__global__ void __launch_bounds__(WARPS * 32)
+gat_delta_kernel(const float4* __restrict__ O, const float4* __restrict__ dO, int64_t lddo4, int64_t n, float* __restrict__ stats) {
+  constexpr int G = 32 / H;
+  const int lane = lane_id();
+  const int64_t i = int64_t(blockIdx.x) * WARPS + warp_id();
+  if (i >= n) return;
+  const float delta = group_sum<G>(dot4(ldg4(dO + i * lddo4 + lane), ldg4(O + i * ROW4 + lane)));
+  if (lane % G == 0) stats[i * (2 * H) + H + lane / G] = delta;
+}
+
 DropArgs make_drop(float p, uint64_t seed) {
   DropArgs d;
   d.seed = seed;
@@ -314,6 +327,23 @@ extern "C" int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, con
     PC_DISPATCH_HEADS(heads, false, CALL_BS)
   }
 #undef CALL_BS
+  PC_LAUNCH_CHECK();
+  return PC_OK;
+}
+
+extern "C" int pc_gat_delta(const float* o, const float* d_o, int64_t ld_do, int64_t n, int heads, float* stats,
+                            pc_stream_t stream) {
+  if (int rc = check_common(o, d_o, stats, stats, n, heads, 0.f)) return rc;
+  PC_REQUIRE(ld_do >= 128 && ld_do % 4 == 0, PC_ERR_INVALID, "gat_delta: bad leading dimension");
+  if (n == 0) return PC_OK;
+  const unsigned grid = unsigned(ceil_div(n, WARPS));
+  cudaStream_t st = as_stream(stream);
+  switch (heads) {
+    case 1: gat_delta_kernel<1><<<grid, WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(o), reinterpret_cast<const float4*>(d_o), ld_do / 4, n, stats); break;
+    case 2: gat_delta_kernel<2><<<grid, WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(o), reinterpret_cast<const float4*>(d_o), ld_do / 4, n, stats); break;
+    case 4: gat_delta_kernel<4><<<grid, WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(o), reinterpret_cast<const float4*>(d_o), ld_do / 4, n, stats); break;
+    default: gat_delta_kernel<8><<<grid, WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(o), reinterpret_cast<const float4*>(d_o), ld_do / 4, n, stats); break;
+  }
   PC_LAUNCH_CHECK();
   return PC_OK;
 }

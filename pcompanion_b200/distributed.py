@@ -72,20 +72,22 @@ class HaloPlan:
             return ops.unique_sorted(keys)
         return torch.unique(col)
 
-    def _a2a(self, out, inp, out_splits, in_splits):
+    def _a2a(self, out, inp, out_splits, in_splits, async_op: bool = False):
         if self.world == 1:
             out.copy_(inp)
-            return
-        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.group)
+            return None
+        return dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.group,
+                                      async_op=async_op)
 
     # rows travel as [n, width] fp32; splits are in rows
-    def forward_exchange(self, send_rows: torch.Tensor, recv_rows: torch.Tensor) -> None:
-        """send_rows = table[send_idx] (grouped by peer) -> recv_rows [n_halo, width] (grouped by owner)."""
-        self._a2a(recv_rows, send_rows, self.recv_counts, self.send_counts)
+    def forward_exchange(self, send_rows: torch.Tensor, recv_rows: torch.Tensor, async_op: bool = False):
+        """send_rows = table[send_idx] (grouped by peer) -> recv_rows [n_halo, width] (grouped by owner).
+        async_op=True returns the collective's work handle (wait() before the rows are read)."""
+        return self._a2a(recv_rows, send_rows, self.recv_counts, self.send_counts, async_op)
 
-    def reverse_exchange(self, halo_grads: torch.Tensor, returned: torch.Tensor) -> None:
+    def reverse_exchange(self, halo_grads: torch.Tensor, returned: torch.Tensor, async_op: bool = False):
         """halo_grads [n_halo, width] -> returned [n_send, width], row i belongs to local row send_idx[i]."""
-        self._a2a(returned, halo_grads, self.send_counts, self.recv_counts)
+        return self._a2a(returned, halo_grads, self.send_counts, self.recv_counts, async_op)
 
     def halo_bytes(self, width: int = 256) -> int:
         return self.n_halo * width * 4

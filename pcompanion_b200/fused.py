@@ -68,9 +68,15 @@ class _P2VGraphLayer(torch.autograd.Function):
         qg = torch.empty(n, 256, dtype=F32, device=x.device)
         n_ext = graph.n_cols
         kv = torch.empty(n_ext, 256, dtype=F32, device=x.device)
-        ops.linear_tc(h, w_in, b_in, split=128, out0=qg[:, :128], out1=kv[:n])
-        if plan is not None:
-            plan.forward_exchange(ops.rows_gather(kv[:n], plan.send_idx), kv[n:])
+        if plan is None:
+            ops.linear_tc(h, w_in, b_in, split=128, out0=qg[:, :128], out1=kv[:n])
+        else:
+            # K|V first, start the halo all-to-all, project Q while the rows travel
+            ops.linear_tc(h, w_in[128:], b_in[128:], out0=kv[:n])
+            work = plan.forward_exchange(ops.rows_gather(kv[:n], plan.send_idx), kv[n:], async_op=True)
+            ops.linear_tc(h, w_in[:128], b_in[:128], out0=qg[:, :128])
+            if work is not None:
+                work.wait()
         o, stats = ops.gat_fwd_raw(qg[:, :128], kv, graph, heads, p_drop, seed)
         emb = ops.linear_tc(o, w_o, b_o, ops.EPI_BIAS_SELECT, aux=h, rowptr=graph.rowptr)
         ctx.save_for_backward(x, z1, a1, a2, h, qg, kv, o, stats, mean, rstd, gamma, w0, w3, w5, w_in, w_o)
@@ -96,21 +102,27 @@ class _P2VGraphLayer(torch.autograd.Function):
             dw_in, db_in = ops.wgrad_tc(dqkv, h)
             d_h = ops.linear_tc(dqkv, w_in.t().contiguous(), None, ops.EPI_BIAS_ADD, aux=d_rest)
         else:
+            # src-major pass first: its halo rows start travelling back to their owners while the dst-major
+            # pass and the Q-side GEMMs run (the all-to-all is asynchronous on NCCL's stream)
             dq = torch.empty(n, 128, dtype=F32, device=x.device)
             dkv = torch.empty(graph.n_cols, 256, dtype=F32, device=x.device)
-            ops.gat_bwd_raw(qg[:, :128], kv, graph, heads, p_drop, seed, o, qg[:, 128:], stats, dq, dkv)
+            ops.gat_delta_raw(o, qg[:, 128:], heads, stats)
+            ops.gat_bwd_src_raw(qg[:, :128], kv, graph, heads, p_drop, seed, qg[:, 128:], stats, dkv)
             returned = torch.empty(plan.send_idx.numel(), 256, dtype=F32, device=x.device)
-            plan.reverse_exchange(dkv[n:], returned)
+            work = plan.reverse_exchange(dkv[n:], returned, async_op=True)
+            ops.gat_bwd_dst_raw(qg[:, :128], kv, graph, heads, p_drop, seed, o, qg[:, 128:], stats, dq)
+            dw_q, db_q = ops.wgrad_tc(dq, h)
+            w_in_t = w_in.t().contiguous()                                            # [128, 384]
+            d_h = ops.linear_tc(dq, w_in_t[:, :128].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_rest)
+            if work is not None:
+                work.wait()
             off = 0
             for cnt in plan.send_counts:      # fixed peer order, unique ids per peer: deterministic
                 if cnt:
                     ops.rows_scatter_add_(dkv, plan.send_idx[off: off + cnt], returned[off: off + cnt])
                 off += cnt
-            dw_q, db_q = ops.wgrad_tc(dq, h)
             dw_kv, db_kv = ops.wgrad_tc(dkv[:n], h)
             dw_in, db_in = torch.cat([dw_q, dw_kv]), torch.cat([db_q, db_kv])
-            w_in_t = w_in.t().contiguous()                                            # [128, 384]
-            d_h = ops.linear_tc(dq, w_in_t[:, :128].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_rest)
             d_h = ops.linear_tc(dkv[:n], w_in_t[:, 128:].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_h)
         # FFN
         dw5, db5 = ops.wgrad_tc(d_h, a2)

@@ -174,15 +174,28 @@ def gat_fwd_raw(q: torch.Tensor, kv: torch.Tensor, graph: "CSRGraph", heads: int
     return o, stats
 
 
-def gat_bwd_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, o, d_o, stats, dq, dkv) -> None:
-    """pc_gat_bwd_dst + pc_gat_bwd_src; q, d_o, dq, dkv may be strided views (row strides are passed down)."""
+def gat_delta_raw(o, d_o, heads, stats) -> None:
+    call("pc_gat_delta", dev(o, F32, "o"), _f32_cuda(d_o, "d_o"), d_o.stride(0), o.shape[0], heads, dev(stats, F32, "stats"), stream())
+
+
+def gat_bwd_dst_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, o, d_o, stats, dq) -> None:
     call("pc_gat_bwd_dst", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(graph.rowptr, I64, "rowptr"),
          dev(graph.col, I32, "col"), graph.n_rows, heads, float(dropout_p), int(seed), dev(o, F32, "o"),
          _f32_cuda(d_o, "d_o"), d_o.stride(0), dev(stats, F32, "stats"), _f32_cuda(dq, "dq"), dq.stride(0), stream())
+
+
+def gat_bwd_src_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, d_o, stats, dkv) -> None:
+    """needs stats[:,1,:] (delta) from pc_gat_bwd_dst or pc_gat_delta"""
     colptr, row = graph.transposed()
     call("pc_gat_bwd_src", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(colptr, I64, "colptr"),
          dev(row, I32, "row"), graph.n_cols, heads, float(dropout_p), int(seed), _f32_cuda(d_o, "d_o"), d_o.stride(0),
          dev(stats, F32, "stats"), _f32_cuda(dkv, "dkv"), dkv.stride(0), stream())
+
+
+def gat_bwd_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, o, d_o, stats, dq, dkv) -> None:
+    """pc_gat_bwd_dst + pc_gat_bwd_src; q, d_o, dq, dkv may be strided views (row strides are passed down)."""
+    gat_bwd_dst_raw(q, kv, graph, heads, dropout_p, seed, o, d_o, stats, dq)
+    gat_bwd_src_raw(q, kv, graph, heads, dropout_p, seed, d_o, stats, dkv)
 
 
 class _GATAttention(torch.autograd.Function):
