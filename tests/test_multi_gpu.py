@@ -53,10 +53,12 @@ def _worker(rank, world, port, results):
         allreduce_gradients(model2)
         err = (out - out_full[b0:b1]).abs().max().item() / out_full.abs().max().item()
         assert err < 1e-6, f"partitioned forward differs: {err}"
+        w0_scale = ref_grads[0].abs().max().item()
         for (k, p), r in zip(model2.named_parameters(), ref_grads):
-            scale = r.abs().max().item() + 1e-12
+            # ffn.0.bias sits in front of BatchNorm: its gradient is mathematically zero, only summation noise
+            scale = w0_scale if k == "ffn.0.bias" else r.abs().max().item() + 1e-12
             e = (p.grad - r).abs().max().item() / scale
-            assert e < (1e-3 if k == "ffn.0.bias" else 2e-5), f"grad {k} differs: {e}"
+            assert e < 2e-5, f"grad {k} differs: {e}"
         assert torch.allclose(model2.ffn[1].running_mean, ref_rm, rtol=1e-6, atol=1e-7)
         # sharded retrieval == unsharded, bit for bit
         cat = torch.tensor(rng.normal(size=(20000, 128)).astype(np.float32), device=dev)
