@@ -56,11 +56,31 @@ __device__ __forceinline__ void warp_topk_insert(Cand& mine, int k, double s, in
 
 constexpr int RB = 8;            // score rows per group
 constexpr int DCH = 32;          // dims per staged chunk
-constexpr int TILE_LD = 34;      // doubles per staged product chunk (32 + 2 pad: conflict-free LDS.128 across lanes)
+constexpr int TILE_LD = 36;      // floats per staged product chunk (32 + 4 pad: conflict-free LDS.128 across lanes)
+constexpr int TILE_FLOATS = 32 * TILE_LD;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 16 : 0;   // src-size 0 => the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+// stage the 32-dim chunk `d0` of the warp's 32 products: 8 lanes cover the 128-byte piece of one product
+__device__ __forceinline__ void stage_chunk(float* tile, const float* __restrict__ catalog, int dim, int d0, int member) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int prod = j * 4 + (lane >> 3);
+    const int m = __shfl_sync(FULL, member, prod);
+    const float* src = catalog + (m >= 0 ? int64_t(m) * dim + d0 + (lane & 7) * 4 : 0);
+    cp_async16(tile + prod * TILE_LD + (lane & 7) * 4, src, m >= 0);
+  }
+}
 
 // grid = (splits, n_groups).  Group g = score rows row_ids[grp_begin[g] .. grp_begin[g+1]) (<= RB), all ranking
-// members[seg_begin[g] .. seg_end[g]).  Lane = one product of a 32-product batch; chunks of 32 dims are staged
-// through shared memory with coalesced loads, then every lane runs RB sequential fp64 dot products.
+// members[seg_begin[g] .. seg_end[g]).  Lane = one product of a 32-product batch; 32-dim chunks are staged
+// through shared memory with cp.async (double-buffered, coalesced), then every lane advances RB independent
+// sequential fp64 dot products (the RB chains interleave, which is what keeps the fp64 pipe busy).
 __global__ void __launch_bounds__(TK_WARPS * 32)
 topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
                    const int32_t* __restrict__ members, const int32_t* __restrict__ row_ids,
@@ -68,9 +88,9 @@ topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict
                    const int64_t* __restrict__ seg_end, int k, int splits, int64_t index_base,
                    double* __restrict__ part_s, int64_t* __restrict__ part_i) {
   extern __shared__ double smem_d[];
-  double* q_s = smem_d;                                              // [RB][dim]
-  double* tiles = q_s + RB * dim;                                    // [TK_WARPS][32][TILE_LD], converted to fp64 once
-  Cand* lists = reinterpret_cast<Cand*>(tiles + TK_WARPS * 32 * TILE_LD);   // [TK_WARPS][RB][32]
+  double* q_s = smem_d;                                                      // [RB][dim], rows >= n_rows are zero
+  float* tiles = reinterpret_cast<float*>(q_s + RB * dim);                   // [TK_WARPS][2][32][TILE_LD]
+  Cand* lists = reinterpret_cast<Cand*>(tiles + TK_WARPS * 2 * TILE_FLOATS); // [TK_WARPS][RB][32]
   const int lane = lane_id(), w = warp_id();
   const int g = blockIdx.y, split = blockIdx.x;
   const int r_beg = grp_begin[g], n_rows = grp_begin[g + 1] - r_beg;
@@ -87,54 +107,51 @@ topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict
   Cand mine[RB];
 #pragma unroll
   for (int r = 0; r < RB; ++r) mine[r] = Cand{-INFINITY, -1};
-  double* tile = tiles + w * 32 * TILE_LD;
-  for (int64_t base = sb + int64_t(w) * 32; base < se; base += TK_WARPS * 32) {
-    const int64_t my_pos = base + lane;
-    int64_t my_member = -1;
-    if (my_pos < se) my_member = members ? int64_t(members[my_pos]) : my_pos;
+  float* tile = tiles + w * 2 * TILE_FLOATS;
+  const int n_chunks = dim / DCH;
+  auto member_at = [&](int64_t pos) -> int { return pos < se ? (members ? members[pos] : int(pos)) : -1; };
+
+  int64_t base = sb + int64_t(w) * 32;
+  int cur = member_at(base + lane);
+  int buf = 0;
+  if (base < se) stage_chunk(tile, catalog, dim, 0, cur);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  while (base < se) {
+    const int64_t next_base = base + TK_WARPS * 32;
+    const int nxt = member_at(next_base + lane);
     double acc[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r] = 0.0;
-    for (int d0 = 0; d0 < dim; d0 += DCH) {
-      // coalesced staging: 8 lanes cover the 128-byte chunk of one product, 4 products per instruction;
-      // the float -> double conversion happens here, once per element, not once per (row, element)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int prod = j * 4 + (lane >> 3);
-        const int64_t m = __shfl_sync(FULL, (long long)my_member, prod);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m >= 0) v = ld_stream4(reinterpret_cast<const float4*>(catalog + m * dim + d0) + (lane & 7));
-        double2* dst = reinterpret_cast<double2*>(tile + prod * TILE_LD + (lane & 7) * 4);
-        dst[0] = make_double2(double(v.x), double(v.y));
-        dst[1] = make_double2(double(v.z), double(v.w));
-      }
+    for (int c = 0; c < n_chunks; ++c) {
+      if (c + 1 < n_chunks) stage_chunk(tile + (buf ^ 1) * TILE_FLOATS, catalog, dim, (c + 1) * DCH, cur);
+      else if (next_base < se) stage_chunk(tile + (buf ^ 1) * TILE_FLOATS, catalog, dim, 0, nxt);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncwarp();
+      const float* mine_c = tile + buf * TILE_FLOATS + lane * TILE_LD;
+      const double* qq = q_s + c * DCH;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         double cd[DCH / 2];
 #pragma unroll
-        for (int j = 0; j < DCH / 4; ++j) {
-          const double2 v = *reinterpret_cast<const double2*>(tile + lane * TILE_LD + half * (DCH / 2) + 2 * j);
-          cd[2 * j] = v.x; cd[2 * j + 1] = v.y;
+        for (int j = 0; j < DCH / 8; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(mine_c + half * (DCH / 2) + 4 * j);
+          cd[4 * j] = double(v.x); cd[4 * j + 1] = double(v.y); cd[4 * j + 2] = double(v.z); cd[4 * j + 3] = double(v.w);
         }
 #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          if (r < n_rows) {
-            const double* qq = q_s + r * dim + d0 + half * (DCH / 2);
-            double a = acc[r];
+        for (int dd = 0; dd < DCH / 2; dd += 2) {
 #pragma unroll
-            for (int dd = 0; dd < DCH / 2; dd += 2) {
-              const double2 q2 = *reinterpret_cast<const double2*>(qq + dd);
-              a = fma(q2.x, cd[dd], a);
-              a = fma(q2.y, cd[dd + 1], a);
-            }
-            acc[r] = a;
+          for (int r = 0; r < RB; ++r) {   // RB independent accumulation chains, each sequential in d
+            const double2 q2 = *reinterpret_cast<const double2*>(qq + r * dim + half * (DCH / 2) + dd);
+            acc[r] = fma(q2.x, cd[dd], acc[r]);
+            acc[r] = fma(q2.y, cd[dd + 1], acc[r]);
           }
         }
       }
       __syncwarp();
+      buf ^= 1;
     }
-    const int64_t gidx = my_member >= 0 ? my_member + index_base : -1;
+    const int64_t gidx = cur >= 0 ? int64_t(cur) + index_base : -1;
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       if (r < n_rows) {
@@ -148,7 +165,10 @@ topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict
         }
       }
     }
+    base = next_base;
+    cur = nxt;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int r = 0; r < RB; ++r) lists[(w * RB + r) * 32 + lane] = mine[r];
   __syncthreads();
@@ -267,7 +287,7 @@ extern "C" int pc_topk_groups(const float* q, int64_t rows, int dim, const float
   PC_REQUIRE(dim >= DCH && dim % DCH == 0 && dim <= 1024, PC_ERR_UNSUPPORTED, "topk_groups: dim=%d must be a multiple of %d (<= 1024)", dim, DCH);
   PC_REQUIRE(splits >= 1 && splits <= 65535, PC_ERR_UNSUPPORTED, "topk_groups: bad splits");
   cudaStream_t st = as_stream(stream);
-  const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 32 * TILE_LD * sizeof(double) +
+  const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 2 * TILE_FLOATS * sizeof(float) +
                       size_t(TK_WARPS) * RB * 32 * sizeof(Cand);
   static bool configured = false;
   if (!configured) {
