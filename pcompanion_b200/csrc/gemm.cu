@@ -61,6 +61,7 @@ struct LinearParams {
   int epilogue;
   const float* aux; int ld_aux;      // EPI_TANH_GRAD: tanh output t (y = acc * (1 - t^2)); EPI_BIAS_SELECT: fallback rows
   const int64_t* rowptr;             // EPI_BIAS_SELECT: row keeps acc + bias iff rowptr[r+1] > rowptr[r]
+  int bsplit;                        // 1: the weight tile is loaded raw and split in the kernel (less L2 -> SM traffic)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -122,10 +123,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// round-to-nearest (ties away) to tf32 on the integer pipe: add half an ulp of the 10-bit mantissa, clear the low
+// 13 bits.  Same result as cvt.rna.tf32.f32 for finite values, but cvt runs on the quarter-rate conversion pipe
+// and was the limiter of the operand-split warps (profiles/: forward GEMM 28 % slower when it also split W).
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // K-major operand tile, 128-byte swizzle, rows of 128 bytes, 8-row groups 1024 bytes apart
@@ -164,7 +166,8 @@ __global__ void split_tf32_kernel(const float4* __restrict__ w, int64_t n4, floa
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
-                     const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_out0,
+                     const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_wraw,
+                     const __grid_constant__ CUtensorMap map_out0,
                      const __grid_constant__ CUtensorMap map_out1, const LinearParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -178,18 +181,20 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t lo_empty = smem_u32(bars + 3 * A_STAGES), b_full = smem_u32(bars + 3 * A_STAGES + LO_STAGES);
   const uint32_t b_empty = smem_u32(bars + 3 * A_STAGES + LO_STAGES + B_STAGES);
   const uint32_t tfull_bar = smem_u32(bars + 3 * A_STAGES + LO_STAGES + 2 * B_STAGES), tempty_bar = tfull_bar + 16;
+  const uint32_t b_ready = tempty_bar + 16;
   const int warp = warp_id(), lane = lane_id();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(a_full + 8 * s, 1);
-      mbar_init(a_ready + 8 * s, SPLIT_THREADS);
+      mbar_init(a_ready + 8 * s, SPLIT_THREADS / 32);
       mbar_init(a_empty + 8 * s, 1);
     }
     for (int s = 0; s < LO_STAGES; ++s) mbar_init(lo_empty + 8 * s, 1);
     for (int s = 0; s < B_STAGES; ++s) {
       mbar_init(b_full + 8 * s, 1);
       mbar_init(b_empty + 8 * s, 1);
+      mbar_init(b_ready + 8 * s, SPLIT_THREADS / 32);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
@@ -235,9 +240,14 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(b_empty + 8 * rb.stage, rb.phase ^ 1);
           uint8_t* st = smem + OFF_B + rb.stage * 2 * B_BYTES;
-          mbar_arrive_expect_tx(b_full + 8 * rb.stage, 2 * b_tile_bytes);
-          tma_load_2d(smem_u32(st), &map_whi, kb * BK, n0, b_full + 8 * rb.stage);
-          tma_load_2d(smem_u32(st + B_BYTES), &map_wlo, kb * BK, n0, b_full + 8 * rb.stage);
+          if (p.bsplit) {
+            mbar_arrive_expect_tx(b_full + 8 * rb.stage, b_tile_bytes);
+            tma_load_2d(smem_u32(st), &map_wraw, kb * BK, n0, b_full + 8 * rb.stage);
+          } else {
+            mbar_arrive_expect_tx(b_full + 8 * rb.stage, 2 * b_tile_bytes);
+            tma_load_2d(smem_u32(st), &map_whi, kb * BK, n0, b_full + 8 * rb.stage);
+            tma_load_2d(smem_u32(st + B_BYTES), &map_wlo, kb * BK, n0, b_full + 8 * rb.stage);
+          }
           rb.advance();
         }
       }
@@ -255,7 +265,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tc_fence_after();
       const uint32_t d_main = tmem_base + uint32_t(acc * 2 * MAX_BN), d_cross = d_main + MAX_BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(b_full + 8 * rb.stage, rb.phase);
+        mbar_wait((p.bsplit ? b_ready : b_full) + 8 * rb.stage, rb.phase);
         mbar_wait(a_ready + 8 * ra.stage, ra.phase);
         tc_fence_after();
         if (lane == 0) {
@@ -290,9 +300,26 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ---------------- activation split: hi = rn_tf32(x) in place, lo = x - hi into the lo ring
     Ring<A_STAGES> ra;
     Ring<LO_STAGES> rl;
+    Ring<B_STAGES> rb;
     const int tid = threadIdx.x - 256;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       for (int kb = 0; kb < k_blocks; ++kb) {
+        if (p.bsplit) {   // weight tile: hi in place, lo right behind it
+          mbar_wait(b_full + 8 * rb.stage, rb.phase);
+          uint8_t* bh = smem + OFF_B + rb.stage * 2 * B_BYTES;
+          for (int i = tid; i < int(b_tile_bytes / 16); i += SPLIT_THREADS) {
+            const float4 v = *reinterpret_cast<const float4*>(bh + i * 16);
+            float4 h, l;
+            h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+            l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+            *reinterpret_cast<float4*>(bh + i * 16) = h;
+            *reinterpret_cast<float4*>(bh + B_BYTES + i * 16) = l;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_ready + 8 * rb.stage);
+          rb.advance();
+        }
         mbar_wait(a_full + 8 * ra.stage, ra.phase);
         mbar_wait(lo_empty + 8 * rl.stage, rl.phase ^ 1);
         uint8_t* hi_base = smem + ra.stage * A_BYTES;
@@ -307,7 +334,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           *reinterpret_cast<float4*>(lo_base + i * 16) = l;
         }
         fence_proxy_async();
-        mbar_arrive(a_ready + 8 * ra.stage);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready + 8 * ra.stage);
         ra.advance();
         rl.advance();
       }
@@ -399,12 +427,14 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // accumulators (hi.hi and cross terms) are added, rounded, into the CTA's fp32 partial in
 // global memory.  A second kernel sums the partials in CTA order (deterministic, no atomics).
 constexpr int WG_ROWS = 16;                        // reduction rows per stage (2 x UMMA_K)
-constexpr int WG_STAGES = 4;
+constexpr int WG_STAGES = 6;                       // raw tiles from HBM (they become the hi tiles in place)
+constexpr int WG_LO_STAGES = 2;                    // lo tiles live only between the split and the MMA
 constexpr int WG_MAX_K = 256;
 constexpr int WG_DY_BYTES = BM * WG_ROWS * 4;      // 8 KB: 128 columns x 16 rows
 constexpr int WG_X_BYTES = WG_MAX_K * WG_ROWS * 4; // 16 KB
-constexpr int WG_STAGE_BYTES = 2 * WG_DY_BYTES + 2 * WG_X_BYTES;   // 48 KB
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + SMEM_MISC;
+constexpr int WG_STAGE_BYTES = WG_DY_BYTES + WG_X_BYTES;           // 24 KB
+constexpr int WG_OFF_LO = WG_STAGES * WG_STAGE_BYTES;
+constexpr int WG_SMEM = (WG_STAGES + WG_LO_STAGES) * WG_STAGE_BYTES + 1024 + SMEM_MISC;   // 192 KB + misc
 constexpr int WG_GROUP_BYTES = WG_ROWS * 128;      // one 32-column group of a stage
 constexpr int WG_FLUSH = 32;                       // blocks per accumulation chain
 
@@ -432,34 +462,28 @@ __device__ __forceinline__ uint32_t instr_desc_tf32_mn(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
 }
 
-struct WgPipe {
-  int stage = 0;
-  uint32_t phase = 0;
-  __device__ __forceinline__ void advance() {
-    if (++stage == WG_STAGES) {
-      stage = 0;
-      phase ^= 1;
-    }
-  }
-};
+using WgPipe = Ring<WG_STAGES>;
+using WgLoPipe = Ring<WG_LO_STAGES>;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                     const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* misc = smem + WG_STAGES * WG_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // full[4], ready[4], empty[4], tmem_full, tmem_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-  const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + 4), empty_bar = smem_u32(bars + 8);
-  const uint32_t tfull_bar = smem_u32(bars + 12), tempty_bar = smem_u32(bars + 13);
+  uint8_t* misc = smem + (WG_STAGES + WG_LO_STAGES) * WG_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // full[6], ready[6], empty[6], lo_empty[2], tmem_full, tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
+  const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + WG_STAGES), empty_bar = smem_u32(bars + 2 * WG_STAGES);
+  const uint32_t lo_empty_bar = smem_u32(bars + 3 * WG_STAGES);
+  const uint32_t tfull_bar = lo_empty_bar + 8 * WG_LO_STAGES, tempty_bar = tfull_bar + 8;
   const int warp = warp_id(), lane = lane_id();
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(ready_bar + 8 * s, SPLIT_THREADS);
+      mbar_init(ready_bar + 8 * s, SPLIT_THREADS / 32);
       mbar_init(empty_bar + 8 * s, 1);
     }
+    for (int s = 0; s < WG_LO_STAGES; ++s) mbar_init(lo_empty_bar + 8 * s, 1);
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -487,12 +511,13 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
         uint8_t* st = smem + pipe.stage * WG_STAGE_BYTES;
         mbar_arrive_expect_tx(full_bar + 8 * pipe.stage, WG_DY_BYTES + x_bytes);
         tma_load_3d(smem_u32(st), &map_dy, 0, row0, half * 4, full_bar + 8 * pipe.stage);
-        tma_load_3d(smem_u32(st + 2 * WG_DY_BYTES), &map_x, 0, row0, 0, full_bar + 8 * pipe.stage);
+        tma_load_3d(smem_u32(st + WG_DY_BYTES), &map_x, 0, row0, 0, full_bar + 8 * pipe.stage);
         pipe.advance();
       }
     }
   } else if (warp == 1) {
     WgPipe pipe;
+    WgLoPipe lo;
     const uint32_t idesc = instr_desc_tf32_mn(p.k);
     const uint32_t d_main = tmem_base, d_cross = tmem_base + WG_MAX_K;
     uint32_t flush_phase = 0;
@@ -506,27 +531,31 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
       tc_fence_after();
       if (lane == 0) {
         const uint32_t st = smem_u32(smem + pipe.stage * WG_STAGE_BYTES);
+        const uint32_t sl = smem_u32(smem + WG_OFF_LO + lo.stage * WG_STAGE_BYTES);
 #pragma unroll
         for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
-          const uint64_t a_hi = smem_desc_mn_sw128(st + ks * 1024), a_lo = smem_desc_mn_sw128(st + WG_DY_BYTES + ks * 1024);
-          const uint64_t b_hi = smem_desc_mn_sw128(st + 2 * WG_DY_BYTES + ks * 1024);
-          const uint64_t b_lo = smem_desc_mn_sw128(st + 2 * WG_DY_BYTES + WG_X_BYTES + ks * 1024);
+          const uint64_t a_hi = smem_desc_mn_sw128(st + ks * 1024), a_lo = smem_desc_mn_sw128(sl + ks * 1024);
+          const uint64_t b_hi = smem_desc_mn_sw128(st + WG_DY_BYTES + ks * 1024);
+          const uint64_t b_lo = smem_desc_mn_sw128(sl + WG_DY_BYTES + ks * 1024);
           const uint32_t accum = (in_chain | ks) != 0;
           umma_tf32(d_cross, a_lo, b_hi, idesc, accum);
           umma_tf32(d_cross, a_hi, b_lo, idesc, 1);
           umma_tf32(d_main, a_hi, b_hi, idesc, accum);
         }
         umma_commit(empty_bar + 8 * pipe.stage);
+        umma_commit(lo_empty_bar + 8 * lo.stage);
         if (in_chain == WG_FLUSH - 1 || i == my_blocks - 1) umma_commit(tfull_bar);
       }
       __syncwarp();
       if (in_chain == WG_FLUSH - 1) flush_phase ^= 1;
       pipe.advance();
+      lo.advance();
     }
   } else if (warp >= 8) {
     // split hi/lo; a thread owns one (32-column group, 16-byte chunk, 8-row half) item of dY or X, so the dY
     // column sums stay in its registers
     WgPipe pipe;
+    WgLoPipe lo;
     const int tid = threadIdx.x - 256;
     const int dy_items = (BM / 4) * 2, x_items = (p.k / 4) * 2;   // 64 + up to 128 <= 256 threads
     const bool active = tid < dy_items + x_items;
@@ -534,29 +563,33 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
     const int item = is_dy ? tid : tid - dy_items;
     const int pair = item >> 1, r0 = (item & 1) * 8;
     const int c = pair & 7;
-    const uint32_t op_off = (is_dy ? 0u : uint32_t(2 * WG_DY_BYTES)) + uint32_t(pair >> 3) * WG_GROUP_BYTES;
-    const uint32_t lo_off = is_dy ? uint32_t(WG_DY_BYTES) : uint32_t(WG_X_BYTES);
+    const uint32_t op_off = (is_dy ? 0u : uint32_t(WG_DY_BYTES)) + uint32_t(pair >> 3) * WG_GROUP_BYTES;
     float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t i = 0; i < my_blocks; ++i) {
       mbar_wait(full_bar + 8 * pipe.stage, pipe.phase);
+      mbar_wait(lo_empty_bar + 8 * lo.stage, lo.phase ^ 1);
       if (active) {
         uint8_t* base = smem + pipe.stage * WG_STAGE_BYTES + op_off;
+        uint8_t* lo_base = smem + WG_OFF_LO + lo.stage * WG_STAGE_BYTES + op_off;
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
           const int r = r0 + rr;
-          uint8_t* hi_p = base + r * 128 + (((((c >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4);
+          const uint32_t off = uint32_t(r * 128 + (((((c >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4));
+          uint8_t* hi_p = base + off;
           const float4 v = *reinterpret_cast<const float4*>(hi_p);
           float4 h, l;
           h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
           l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
           *reinterpret_cast<float4*>(hi_p) = h;
-          *reinterpret_cast<float4*>(hi_p + lo_off) = l;
+          *reinterpret_cast<float4*>(lo_base + off) = l;
           colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w;
         }
       }
       fence_proxy_async();
-      mbar_arrive(ready_bar + 8 * pipe.stage);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready_bar + 8 * pipe.stage);
       pipe.advance();
+      lo.advance();
     }
     if (p.partial_b && is_dy) {
       // logical chunk c of group g covers columns g*32 + 4c .. +3 (the swizzle only permutes positions)
@@ -683,15 +716,19 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   float* w_hi = reinterpret_cast<float*>(workspace);
   float* w_lo = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(size_t(n) * k * sizeof(float), 256));
   const int64_t n4 = int64_t(n) * k / 4;
-  split_tf32_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(w), n4,
-                                                               reinterpret_cast<float4*>(w_hi), reinterpret_cast<float4*>(w_lo));
-  PC_LAUNCH_CHECK();
-  CUtensorMap map_a, map_whi, map_wlo;
+  {
+    split_tf32_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(w), n4,
+                                                                 reinterpret_cast<float4*>(w_hi), reinterpret_cast<float4*>(w_lo));
+    PC_LAUNCH_CHECK();
+  }
+  // measured (profiles/gemm_microbench.py): pre-split weights (0) beat the in-kernel split (1) by ~20 % - the
+  // operand-split warps sit on the critical path, the extra L2 -> SM traffic of the lo tile does not
+  p.bsplit = 0;
+  CUtensorMap map_a, map_whi, map_wlo, map_wraw;
+  if (int rc = make_map(&map_wraw, w, n, k, k, p.bn)) return rc;
   // consecutive K blocks of a row are adjacent in memory: let L2 fetch 256 B per miss so the next block's
   // request hits, halving the DRAM page activations of the strided [128 x 32] activation boxes
-  static const int promo_env = getenv("PC_GEMM_L2PROMO") ? atoi(getenv("PC_GEMM_L2PROMO")) : 256;
-  const CUtensorMapL2promotion promo = promo_env == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo_env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-  if (int rc = make_map(&map_a, a, m, k, lda, BM, promo)) return rc;
+  if (int rc = make_map(&map_a, a, m, k, lda, BM, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return rc;
   if (int rc = make_map(&map_whi, w_hi, n, k, k, p.bn)) return rc;
   if (int rc = make_map(&map_wlo, w_lo, n, k, k, p.bn)) return rc;
   CUtensorMap map_out0, map_out1;
@@ -708,7 +745,7 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   }
   const int64_t tiles = ((m + BM - 1) / BM) * p.n_tiles;
   const int grid = int(tiles < sm_count() ? tiles : sm_count());
-  linear_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out0, map_out1, p);
+  linear_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_wraw, map_out0, map_out1, p);
   PC_LAUNCH_CHECK();
   return PC_OK;
 }
