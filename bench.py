@@ -130,9 +130,7 @@ def run_ours(args):
 
     def step(x, tr):
         emb = model.forward_graph(x, graph)
-        a, p = emb[tr[:, 0]], emb[tr[:, 1]]
-        ng = emb[tr[:, 2:].reshape(-1)].reshape(TRIPLETS, KNEG, -1)
-        loss = model.triplet_loss(a, p, ng)
+        loss = model.triplet_loss_indexed(emb, tr[:, 0], tr[:, 1], tr[:, 2:])
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()

@@ -201,6 +201,11 @@ int pc_topk_merge(const double* scores, const int64_t* idx, int64_t rows, int li
 int pc_rows_gather(const float* table, const int64_t* index, int64_t n, int width, float* out, pc_stream_t stream);
 int pc_rows_scatter_add(const float* rows, const int64_t* index, int64_t n, int width, float* table,
                         pc_stream_t stream);
+/* out[r, :] = sum_{e in [rowptr[r], rowptr[r+1])} rows[col[e], :] in ascending e, zeros for empty rows: the
+ * deterministic gradient of a row gather table[index] (the index list is turned into a CSR with the BPG sort
+ * kernels), used for the embedding rows a triplet batch touches (product2vec.py:132-134 on a shared table). */
+int pc_rows_segment_sum(const float* rows, const int64_t* rowptr, const int32_t* col, int64_t n, int width, float* out,
+                        pc_stream_t stream);
 
 #ifdef __cplusplus
 }

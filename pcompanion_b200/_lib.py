@@ -55,6 +55,7 @@ PROTOTYPES = {
     "pc_topk_merge": (c_int, [P, P, c_int64, c_int, c_int, P, P, P]),
     "pc_rows_gather": (c_int, [P, P, c_int64, c_int, P, P]),
     "pc_rows_scatter_add": (c_int, [P, P, c_int64, c_int, P, P]),
+    "pc_rows_segment_sum": (c_int, [P, P, P, c_int64, c_int, P, P]),
 }
 
 

@@ -57,6 +57,24 @@ rows_scatter_add_kernel(const float4* __restrict__ rows, const int64_t* __restri
   }
 }
 
+// out[r, :] = sum over e in [rowptr[r], rowptr[r+1]) of rows[col[e], :] in ascending e (zeros for empty rows):
+// the deterministic transpose of a row gather (gradient of table[index] without float atomics).
+__global__ void __launch_bounds__(256)
+rows_segment_sum_kernel(const float4* __restrict__ rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                        int64_t n, int width4, float4* __restrict__ out) {
+  const int64_t r = int64_t(blockIdx.x) * 8 + warp_id();
+  if (r >= n) return;
+  const int64_t beg = rowptr[r], end = rowptr[r + 1];
+  for (int c = lane_id(); c < width4; c += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t e = beg; e < end; ++e) {
+      const float4 v = ldg4(rows + int64_t(col[e]) * width4 + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    out[r * width4 + c] = acc;
+  }
+}
+
 }  // namespace
 }  // namespace pc
 
@@ -93,6 +111,17 @@ extern "C" int pc_rows_scatter_add(const float* rows, const int64_t* index, int6
   PC_REQUIRE(table && index && rows, PC_ERR_INVALID, "rows_scatter_add: null pointer");
   rows_scatter_add_kernel<<<unsigned(ceil_div(n, 8)), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(rows), index, n, width / 4, reinterpret_cast<float4*>(table));
+  PC_LAUNCH_CHECK();
+  return PC_OK;
+}
+
+extern "C" int pc_rows_segment_sum(const float* rows, const int64_t* rowptr, const int32_t* col, int64_t n, int width,
+                                   float* out, pc_stream_t stream) {
+  PC_REQUIRE(n >= 0 && width > 0 && width % 4 == 0, PC_ERR_INVALID, "rows_segment_sum: bad n=%lld width=%d", (long long)n, width);
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(rowptr && out, PC_ERR_INVALID, "rows_segment_sum: null pointer");
+  rows_segment_sum_kernel<<<unsigned(ceil_div(n, 8)), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(rows), rowptr, col, n, width / 4, reinterpret_cast<float4*>(out));
   PC_LAUNCH_CHECK();
   return PC_OK;
 }

@@ -177,9 +177,7 @@ def run_partitioned_bench(args, rank: int, world: int, dev: torch.device) -> Non
 
     def step(xd, tr):
         emb = forward_graph_partitioned(model, xd, plan)
-        a, p = emb[tr[:, 0]], emb[tr[:, 1]]
-        ng = emb[tr[:, 2:].reshape(-1)].reshape(B.TRIPLETS, B.KNEG, -1)
-        loss = model.triplet_loss(a, p, ng)
+        loss = model.triplet_loss_indexed(emb, tr[:, 0], tr[:, 1], tr[:, 2:])
         opt.zero_grad(set_to_none=True)
         loss.backward()
         allreduce_gradients(model)

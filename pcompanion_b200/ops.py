@@ -351,6 +351,56 @@ class _HingeRows(torch.autograd.Function):
         return da, dp, dn, None, None, None, None
 
 
+class _TripletFromTable(torch.autograd.Function):
+    """Triplet hinge on rows of one embedding table selected by index (anchors | positives | negatives).
+    Backward returns a dense d_table built without float atomics: the slot list is stably sorted by node
+    (pc_sort_keys), turned into a CSR and summed per node in slot order (pc_rows_segment_sum)."""
+
+    @staticmethod
+    def forward(ctx, table, slot_nodes, batch: int, kneg: int, margin: float, eps: float):
+        table = table.contiguous()
+        rows = rows_gather(table, slot_nodes)                       # [(2 + kneg) * batch, D]
+        d = table.shape[1]
+        per = torch.empty(batch, dtype=F32, device=table.device)
+        loss = torch.empty((), dtype=F32, device=table.device)
+        a, p, n = rows[:batch], rows[batch: 2 * batch], rows[2 * batch:]
+        call("pc_hinge_rows_fwd", dev(a, F32, "a"), dev(p, F32, "p"), dev(n, F32, "n"), batch, 1, kneg, d, margin, eps,
+             dev(per, F32, "per"), dev(loss, F32, "loss"), stream())
+        ctx.save_for_backward(rows, slot_nodes)
+        ctx.cfg = (batch, kneg, margin, eps, table.shape[0])
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, slot_nodes = ctx.saved_tensors
+        batch, kneg, margin, eps, n_nodes = ctx.cfg
+        d = rows.shape[1]
+        g = g.contiguous().to(F32)
+        grads = torch.empty_like(rows)
+        a, p, n = rows[:batch], rows[batch: 2 * batch], rows[2 * batch:]
+        call("pc_hinge_rows_bwd", dev(a, F32, "a"), dev(p, F32, "p"), dev(n, F32, "n"), batch, 1, kneg, d, margin, eps,
+             dev(g, F32, "grad"), dev(grads[:batch], F32, "da"), dev(grads[batch: 2 * batch], F32, "dp"),
+             dev(grads[2 * batch:], F32, "dn"), stream())
+        slots = rows.shape[0]
+        keys = pack_keys(slot_nodes.to(I32), torch.arange(slots, dtype=I32, device=rows.device))
+        node_bytes = max(1, ((max(n_nodes, 2) - 1).bit_length() + 7) // 8)
+        sort_keys_(keys, ((1 << node_bytes) - 1) << 4)             # stable: slots stay ascending inside a node
+        rowptr, col = csr_from_sorted_keys(keys, n_nodes)
+        d_table = torch.empty(n_nodes, d, dtype=F32, device=rows.device)
+        call("pc_rows_segment_sum", dev(grads, F32, "rows"), dev(rowptr, I64, "rowptr"), dev(col, I32, "col"), n_nodes, d,
+             dev(d_table, F32, "out"), stream())
+        return d_table, None, None, None, None, None
+
+
+def triplet_hinge_indexed(table: torch.Tensor, anchor_idx: torch.Tensor, positive_idx: torch.Tensor,
+                          negative_idx: torch.Tensor, margin: float, eps: float = 1e-6) -> torch.Tensor:
+    """triplet_hinge(table[anchor], table[positive], table[negative [B, K]]) with a deterministic dense d_table."""
+    b = anchor_idx.numel()
+    k = negative_idx.numel() // b
+    slot_nodes = torch.cat([anchor_idx.reshape(-1), positive_idx.reshape(-1), negative_idx.reshape(-1)]).to(I64).contiguous()
+    return _TripletFromTable.apply(table, slot_nodes, b, k, float(margin), float(eps))
+
+
 def triplet_hinge(anchor, positive, negative, margin: float, eps: float = 1e-6) -> torch.Tensor:
     """mean relu(margin - ||a-p+eps|| + mean_k ||a-n_k+eps||)  (product2vec.py:137-154)."""
     if negative.dim() == 2:

@@ -146,6 +146,11 @@ class Product2Vec(nn.Module):
         """The loss block of product2vec.py:137-154 as one fused kernel."""
         return ops.triplet_hinge(anchor_emb, positive_emb, negative_emb, self.config.MARGIN)
 
+    def triplet_loss_indexed(self, table, anchor_idx, positive_idx, negative_idx) -> torch.Tensor:
+        """Same loss on rows of a full-graph embedding table picked by index (graph training: the batch is index
+        tensors into forward_graph's output instead of padded feature copies)."""
+        return ops.triplet_hinge_indexed(table, anchor_idx, positive_idx, negative_idx, self.config.MARGIN)
+
     def train_model(self, train_loader, optimizer, num_epochs=10) -> Dict[str, torch.Tensor]:
         """Training loop of product2vec.py:113-170 (same batch keys, same return value)."""
         device = self.config.DEVICE

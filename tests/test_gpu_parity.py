@@ -554,3 +554,26 @@ def test_fused_graph_layer_equals_unfused_path_and_single_rank_partition():
                 close(a, r.double().cpu().numpy(), rel=5e-5, atol=3e-6 if k == "ffn.0.bias" else 1e-7, what=f"{name} grad {k} train={train}")
             close(got[3], ref[3].double().cpu().numpy(), what="running_mean")
             close(got[4], ref[4].double().cpu().numpy(), what="running_var")
+
+
+def test_indexed_triplet_loss_equals_gathered_loss_and_is_deterministic():
+    from pcompanion_b200 import ops
+    g = torch.Generator(device=dev()).manual_seed(8)
+    n, b, k = 5000, 3000, 5
+    table = torch.randn(n, 128, generator=g, device=dev()) * 0.3
+    ai, pi = (torch.randint(0, n, (b,), generator=g, device=dev()) for _ in range(2))
+    ni = torch.randint(0, 40, (b, k), generator=g, device=dev())              # hot rows: many slots per node
+    t1 = table.clone().requires_grad_(True)
+    l1 = ops.triplet_hinge_indexed(t1, ai, pi, ni, 1.0)
+    l1.backward()
+    t2 = table.clone().double().requires_grad_(True)
+    a, p, nn = t2[ai], t2[pi], t2[ni.reshape(-1)].reshape(b, k, 128)
+    dpos = torch.nn.functional.pairwise_distance(a, p)
+    dneg = torch.nn.functional.pairwise_distance(a.unsqueeze(1).expand(-1, k, -1), nn).mean(1)
+    l2 = torch.relu(1.0 - dpos + dneg).mean()
+    l2.backward()
+    close(l1, l2.item(), what="indexed loss")
+    close(t1.grad, t2.grad.cpu().numpy(), what="d table")
+    t3 = table.clone().requires_grad_(True)
+    ops.triplet_hinge_indexed(t3, ai, pi, ni, 1.0).backward()
+    assert torch.equal(t3.grad, t1.grad)                                       # no atomics: bit-reproducible
