@@ -168,6 +168,13 @@ int pc_hinge_type_fwd(const float* sims, const int64_t* pos, const int64_t* neg,
 int pc_hinge_type_bwd(const float* sims, const int64_t* pos, const int64_t* neg, int64_t rows, int64_t n_types,
                       float margin, const float* grad_loss, float* d_sims, pc_stream_t stream);
 
+/* Negative sampling for the triplet batches (data_loader.py:27-40 _get_negative_samples): for every anchor,
+ * k products drawn uniformly that are != anchor, not in the anchor's similar set (row `anchor` of the
+ * similarity-pair CSR, columns ascending) and pairwise distinct; -1 pads when fewer than k exist.
+ * Reproducible from (seed, batch slot). */
+int pc_sample_negatives(const int32_t* anchor, const int64_t* sim_rowptr, const int32_t* sim_col, int64_t batch,
+                        int32_t n_nodes, int k, uint64_t seed, int32_t* out, pc_stream_t stream);
+
 /* ------------------------------------------------------------------ (4) retrieval
  * Replaces torch.matmul + torch.topk of p_companion.py:60-64, metrics.py:21,89 and the
  * per-type filter -> matmul -> topk loop of inference.py:93-113.

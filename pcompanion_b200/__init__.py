@@ -11,6 +11,9 @@ from .bpg import BehaviorProductGraph
 from .p_companion import ComplementaryItemPrediction, ComplementaryTypeTransition, PCompanion
 from .product2vec import Product2Vec
 from .retrieval import CatalogIndex, Metrics, ShardedCatalog
+from .data import ComplementaryDataset, GraphTripletSampler, SimilarityDataset, collate_fn
+from .inference import PCompanionInference
 
 __all__ = ["ops", "BehaviorProductGraph", "Product2Vec", "ComplementaryTypeTransition",
-           "ComplementaryItemPrediction", "PCompanion", "Metrics", "CatalogIndex", "ShardedCatalog"]
+           "ComplementaryItemPrediction", "PCompanion", "Metrics", "CatalogIndex", "ShardedCatalog",
+           "SimilarityDataset", "ComplementaryDataset", "collate_fn", "GraphTripletSampler", "PCompanionInference"]

@@ -245,6 +245,19 @@ def golden_metrics():
         ts, ti = torch.topk(s, k=min(K, len(members)))
         idx[r, :len(ti)] = [members[i] for i in ti.numpy()]
         sc[r, :len(ti)] = ts.numpy()
+    # collate_fn (data_loader.py:171-206) on samples with ragged neighbour lists
+    from src.data.data_loader import collate_fn
+    samples = []
+    for i, nn in enumerate((2, 5, 1, 3)):
+        samples.append({"anchor_ids": f"A{i}", "anchor": torch.randn(8), "positive": torch.randn(8), "negative": torch.randn(5, 8),
+                        "positive_id": f"P{i}", "negative_ids": [f"N{i}{j}" for j in range(5)], "anchor_neighbors": torch.randn(nn, 8)})
+    col = collate_fn(samples)
+    for i, smp in enumerate(samples):
+        for k in ("anchor", "positive", "negative", "anchor_neighbors"):
+            out[f"collate_in/{i}/{k}"] = smp[k].numpy()
+    for k in ("anchor", "positive", "negative", "anchor_neighbors"):
+        out["collate_out/" + k] = col[k].numpy()
+    out["collate_out/anchor_ids"] = np.array(col["anchor_ids"])
     out.update(catalog=catalog.numpy(), type_id=type_id.numpy().astype(np.int32), q=q.numpy(),
                row_type=row_type.numpy().astype(np.int32), topk_idx=idx, topk_score=sc)
     np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)

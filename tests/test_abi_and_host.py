@@ -127,3 +127,27 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.NativeLibraryError, match="no CPU or PyTorch fallback"):
         _lib._load()
+
+
+def test_collate_fn_matches_reference_golden():
+    """collate_fn drop-in vs the real reference's output on ragged neighbour lists (data_loader.py:171-206)."""
+    from pcompanion_b200 import collate_fn
+    g = load_golden("metrics.npz")
+    samples = []
+    for i in range(4):
+        samples.append({"anchor_ids": f"A{i}", "positive_id": f"P{i}", "negative_ids": [f"N{i}{j}" for j in range(5)],
+                        **{k: torch.tensor(g[f"collate_in/{i}/{k}"]) for k in ("anchor", "positive", "negative", "anchor_neighbors")}})
+    out = collate_fn(samples)
+    for k in ("anchor", "positive", "negative", "anchor_neighbors"):
+        assert np.array_equal(out[k].numpy(), g["collate_out/" + k]), k
+    assert out["anchor_ids"] == g["collate_out/anchor_ids"].tolist()
+    assert out["anchor_neighbors"].shape == (4, 5, 8) and float(out["anchor_neighbors"][2, 1:].abs().sum()) == 0.0
+    assert out["negative_ids"][1] == [f"N1{j}" for j in range(5)]
+
+
+def test_similarity_dataset_requires_pairs_like_reference():
+    from pcompanion_b200 import BehaviorProductGraph, SimilarityDataset
+    b = BehaviorProductGraph()
+    b.similarity_pairs = []
+    with pytest.raises(ValueError, match="No similarity pairs found in BPG"):
+        SimilarityDataset(b, make_cfg())
