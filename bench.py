@@ -194,8 +194,16 @@ def run_ours(args):
     abi_calls = {name: len(v) // args.steps for name, v in per_kernel.items()}
     sparse_ms = sum(k["ms"] for k in kernels.values())
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_gat_dram_traffic.json")
+    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        with open(tpath) as f:
+            tj = json.load(f)
+        if dom in tj["kernels"]:
+            traffic, traffic_src = tj["kernels"][dom]["dram_bytes"], "profiles/r1_gat_dram_traffic.json (ncu --set full, same workload)"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algo_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": ALGO_BYTES[dom][0] * e + ALGO_BYTES[dom][1] * n, "peak_source": peak_src,
                 "sparse_fwd_bwd": {"ms": round(sparse_ms, 4),
                                    "algo_gbs": round((3152 * e + 3676 * n) / (sparse_ms * 1e-3) / 1e9, 1),
                                    "frac": round((3152 * e + 3676 * n) / (sparse_ms * 1e-3) / 1e9 / peak, 4)},
