@@ -1,0 +1,425 @@
+// Dense complementary retrieval on the tensor cores: scoring GEMM + per-type mask + top-K, never
+// materialising the [rows, products] score matrix, followed by an exact float64 re-scoring of the
+// surviving candidates.
+//
+// This is the formulation BASELINE.json's north_star words for part (4) ("scored against the whole
+// product embedding catalog with a tensor-core GEMM fused with a per-type mask and a ... top-K"); it
+// replaces torch.matmul + mask + torch.topk of /root/reference/inference.py:101-113 and
+// /root/reference/src/utils/metrics.py:89-100 for rows that rank the WHOLE catalog.  (When every row
+// is restricted to one type, the type-segmented kernel in retrieval.cu does 1/#types of the work and
+// is the default; see DESIGN.md.)
+//
+// Kernel 1 (score_topk_tf32x3_kernel): 128 score rows x 128 products per tile, 3xTF32 tcgen05.mma
+// (fp32-faithful scores, same operand split / two-accumulator scheme as gemm.cu).  A CTA owns one
+// 128-row block and a contiguous range of product tiles ("unit"), so each epilogue thread (= one score
+// row) keeps its own sorted list of the best KP candidates in registers across the whole range; masked
+// products (type_id[p] != row_type[r]) never enter it.  Per unit it writes KP (approx score, index)
+// candidates per row.
+// Kernel 2 (rescore_topk_kernel): one warp per row re-scores the candidates exactly (float64, sequential
+// over d - the score definition of retrieval.cu / oracle/retrieval.py), ranks them (score desc, index
+// asc) and checks the guard band: every product dropped by kernel 1 had an approximate score <= tau (the
+// weakest kept candidate of a full list); if the exact K-th score is not above tau + eps (eps bounds the
+// 3xTF32 error via |q| * max|c|), the row is flagged and the host re-runs it on the exact path.
+#include <math.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int SC_BN = 128;              // products per tile
+constexpr int SC_A_BYTES = BM * BK * 4;
+constexpr int SC_B_BYTES = SC_BN * BK * 4;
+constexpr int SC_A_STAGES = 4, SC_LO_STAGES = 2, SC_B_STAGES = 3;
+constexpr int SC_OFF_LO = SC_A_STAGES * SC_A_BYTES;
+constexpr int SC_OFF_B = SC_OFF_LO + SC_LO_STAGES * SC_A_BYTES;
+constexpr int SC_OPERAND_BYTES = SC_OFF_B + SC_B_STAGES * 2 * SC_B_BYTES;   // 64 + 32 + 96 = 192 KB
+constexpr int SC_THREADS = 512;
+constexpr int SC_SPLIT_THREADS = 256;
+constexpr int SC_SMEM = SC_OPERAND_BYTES + 1024 + 4096;
+constexpr int KP = 16;                  // candidates kept per (row, unit)
+
+struct ScoreParams {
+  int64_t rows, products;
+  int k_blocks;                 // dim / 32
+  int64_t n_tiles;              // ceil(products / 128)
+  int units_per_block;          // S: product ranges per 128-row block
+  int64_t tiles_per_unit;
+  const int32_t* type_id;       // [products] or null
+  const int32_t* row_type;      // [rows] or null (< 0: no restriction)
+  float* part_s;                // [rows, S, KP]
+  int32_t* part_i;              // [rows, S, KP] local product index, -1 = empty
+};
+
+__global__ void __launch_bounds__(SC_THREADS, 1)
+score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
+                         const ScoreParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* misc = smem + SC_OPERAND_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
+  int32_t* types_s = reinterpret_cast<int32_t*>(misc + 512);   // [2][128] product types of the tile in flight
+  const uint32_t a_full = smem_u32(bars + 0), a_ready = smem_u32(bars + SC_A_STAGES), a_empty = smem_u32(bars + 2 * SC_A_STAGES);
+  const uint32_t lo_empty = smem_u32(bars + 3 * SC_A_STAGES), b_full = lo_empty + 8 * SC_LO_STAGES;
+  const uint32_t b_ready = b_full + 8 * SC_B_STAGES, b_empty = b_ready + 8 * SC_B_STAGES;
+  const uint32_t tfull_bar = b_empty + 8 * SC_B_STAGES, tempty_bar = tfull_bar + 16;
+  const int warp = warp_id(), lane = lane_id();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SC_A_STAGES; ++s) {
+      mbar_init(a_full + 8 * s, 1);
+      mbar_init(a_ready + 8 * s, SC_SPLIT_THREADS / 32);
+      mbar_init(a_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < SC_LO_STAGES; ++s) mbar_init(lo_empty + 8 * s, 1);
+    for (int s = 0; s < SC_B_STAGES; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_ready + 8 * s, SC_SPLIT_THREADS / 32);
+      mbar_init(b_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t m_blocks = (p.rows + BM - 1) / BM;
+  const int64_t units = m_blocks * p.units_per_block;
+  // unit u -> 128-row block u / S, product tiles [ (u % S) * tpu, min(n_tiles, (u % S + 1) * tpu) )
+#define SC_FOR_EACH_TILE(...)                                                               \
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {                                 \
+    const int m0 = int((u / p.units_per_block) * BM);                                       \
+    const int range = int(u % p.units_per_block);                                           \
+    const int64_t t_beg = int64_t(range) * p.tiles_per_unit;                                \
+    const int64_t t_end = t_beg + p.tiles_per_unit < p.n_tiles ? t_beg + p.tiles_per_unit : p.n_tiles; \
+    (void)m0;                                                                               \
+    for (int64_t nt = t_beg; nt < t_end; ++nt) {                                            \
+      __VA_ARGS__                                                                           \
+    }                                                                                       \
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring<SC_A_STAGES> ra;
+      SC_FOR_EACH_TILE({
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(a_empty + 8 * ra.stage, ra.phase ^ 1);
+          mbar_arrive_expect_tx(a_full + 8 * ra.stage, SC_A_BYTES);
+          tma_load_2d(smem_u32(smem + ra.stage * SC_A_BYTES), &map_q, kb * BK, m0, a_full + 8 * ra.stage);
+          ra.advance();
+        }
+      })
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      Ring<SC_B_STAGES> rb;
+      SC_FOR_EACH_TILE({
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(b_empty + 8 * rb.stage, rb.phase ^ 1);
+          mbar_arrive_expect_tx(b_full + 8 * rb.stage, SC_B_BYTES);
+          tma_load_2d(smem_u32(smem + SC_OFF_B + rb.stage * 2 * SC_B_BYTES), &map_c, kb * BK, int(nt * SC_BN),
+                      b_full + 8 * rb.stage);
+          rb.advance();
+        }
+      })
+    }
+  } else if (warp == 1) {
+    Ring<SC_A_STAGES> ra;
+    Ring<SC_LO_STAGES> rl;
+    Ring<SC_B_STAGES> rb;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t idesc = instr_desc_tf32(SC_BN);
+    SC_FOR_EACH_TILE({
+      mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + uint32_t(acc * 2 * SC_BN), d_cross = d_main + SC_BN;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(b_ready + 8 * rb.stage, rb.phase);
+        mbar_wait(a_ready + 8 * ra.stage, ra.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t base = smem_u32(smem);
+          const uint64_t a_hi = smem_desc_k_sw128(base + ra.stage * SC_A_BYTES);
+          const uint64_t a_lo = smem_desc_k_sw128(base + SC_OFF_LO + rl.stage * SC_A_BYTES);
+          const uint64_t b_hi = smem_desc_k_sw128(base + SC_OFF_B + rb.stage * 2 * SC_B_BYTES);
+          const uint64_t b_lo = smem_desc_k_sw128(base + SC_OFF_B + rb.stage * 2 * SC_B_BYTES + SC_B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint64_t adv = uint64_t(kk * 32 >> 4);
+            umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | kk) != 0);
+            umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
+          }
+          umma_commit(a_empty + 8 * ra.stage);
+          umma_commit(lo_empty + 8 * rl.stage);
+          umma_commit(b_empty + 8 * rb.stage);
+          if (kb == p.k_blocks - 1) umma_commit(tfull_bar + 8 * acc);
+        }
+        __syncwarp();
+        ra.advance();
+        rl.advance();
+        rb.advance();
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    })
+  } else if (warp >= 8) {
+    // operand split: both tiles raw -> hi in place, lo next to it (queries and catalog are both activations here)
+    Ring<SC_A_STAGES> ra;
+    Ring<SC_LO_STAGES> rl;
+    Ring<SC_B_STAGES> rb;
+    const int tid = threadIdx.x - 256;
+    SC_FOR_EACH_TILE({
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(b_full + 8 * rb.stage, rb.phase);
+        uint8_t* bh = smem + SC_OFF_B + rb.stage * 2 * SC_B_BYTES;
+#pragma unroll
+        for (int i = tid; i < SC_B_BYTES / 16; i += SC_SPLIT_THREADS) {
+          const float4 v = *reinterpret_cast<const float4*>(bh + i * 16);
+          float4 h, l;
+          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+          *reinterpret_cast<float4*>(bh + i * 16) = h;
+          *reinterpret_cast<float4*>(bh + SC_B_BYTES + i * 16) = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_ready + 8 * rb.stage);
+        rb.advance();
+        mbar_wait(a_full + 8 * ra.stage, ra.phase);
+        mbar_wait(lo_empty + 8 * rl.stage, rl.phase ^ 1);
+        uint8_t* ah = smem + ra.stage * SC_A_BYTES;
+        uint8_t* al = smem + SC_OFF_LO + rl.stage * SC_A_BYTES;
+#pragma unroll
+        for (int i = tid; i < SC_A_BYTES / 16; i += SC_SPLIT_THREADS) {
+          const float4 v = *reinterpret_cast<const float4*>(ah + i * 16);
+          float4 h, l;
+          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+          *reinterpret_cast<float4*>(ah + i * 16) = h;
+          *reinterpret_cast<float4*>(al + i * 16) = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready + 8 * ra.stage);
+        ra.advance();
+        rl.advance();
+      }
+    })
+  } else if (warp >= 4) {
+    // ---------------- epilogue: thread = one score row; sorted candidate list (score desc, index asc) in registers
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int quad = warp - 4;
+    const int trow = quad * 32 + lane;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+      const int m0 = int((u / p.units_per_block) * BM);
+      const int range = int(u % p.units_per_block);
+      const int64_t t_beg = int64_t(range) * p.tiles_per_unit;
+      const int64_t t_end = t_beg + p.tiles_per_unit < p.n_tiles ? t_beg + p.tiles_per_unit : p.n_tiles;
+      const int64_t row = int64_t(m0) + trow;
+      const bool row_ok = row < p.rows;
+      const int rt = (p.row_type && row_ok) ? p.row_type[row] : -1;
+      float cs[KP];
+      int32_t ci[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) { cs[j] = -INFINITY; ci[j] = -1; }
+      for (int64_t nt = t_beg; nt < t_end; ++nt) {
+        const int64_t n0 = nt * SC_BN;
+        // stage the tile's product types (-2 = past the end of the catalog)
+        int32_t* ts = types_s + (acc & 1) * SC_BN;
+        {
+          const int64_t pidx = n0 + trow;
+          ts[trow] = pidx < p.products ? (p.type_id ? p.type_id[pidx] : 0) : -2;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tc_fence_after();
+        for (int c0 = 0; c0 < SC_BN; c0 += 32) {
+          uint32_t r[32], rc[32];
+          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * SC_BN + c0), r);
+          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * SC_BN + SC_BN + c0), rc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int t = ts[c0 + j];
+            const bool eligible = row_ok && t != -2 && (rt < 0 || t == rt);
+            const float y = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+            const int32_t idx = int32_t(n0 + c0 + j);
+            if (eligible && (y > cs[KP - 1] || (y == cs[KP - 1] && ci[KP - 1] < 0))) {
+              // insert keeping (score desc, index asc); indices arrive ascending, so equal scores go after
+              float vs = y;
+              int32_t vi = idx;
+              bool shifting = false;
+#pragma unroll
+              for (int q = 0; q < KP; ++q) {
+                if (shifting || vs > cs[q] || ci[q] < 0) {   // first strictly smaller (or empty) slot, then shift the tail
+                  const float tsv = cs[q]; const int32_t tiv = ci[q];
+                  cs[q] = vs; ci[q] = vi;
+                  vs = tsv; vi = tiv;
+                  shifting = true;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar + 8 * acc);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (row < p.rows) {
+        float* os = p.part_s + (row * p.units_per_block + range) * KP;
+        int32_t* oi = p.part_i + (row * p.units_per_block + range) * KP;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) { os[j] = cs[j]; oi[j] = ci[j]; }
+      }
+    }
+  }
+#undef SC_FOR_EACH_TILE
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+struct RCand {
+  double s;
+  int64_t i;
+};
+__device__ __forceinline__ bool r_before(double sa, int64_t ia, double sb, int64_t ib) {
+  if (ib < 0) return ia >= 0;
+  if (ia < 0) return false;
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+// one warp per row: exact float64 re-scoring of the candidates, final ranking, guard-band check
+__global__ void __launch_bounds__(256)
+rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ catalog, int dim, int64_t rows, int units,
+                    const float* __restrict__ part_s, const int32_t* __restrict__ part_i, int k, int64_t index_base,
+                    float max_norm, double* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ flags) {
+  const int64_t r = int64_t(blockIdx.x) * 8 + warp_id();
+  if (r >= rows) return;
+  const int lane = lane_id();
+  const float* q = Q + r * dim;
+  RCand mine{-INFINITY, -1};
+  float tau = -INFINITY;
+  double qn = 0.0;
+  for (int d = lane; d < dim; d += 32) qn += double(q[d]) * double(q[d]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(FULL, qn, o);
+  const int total = units * KP;
+  for (int base = 0; base < total; base += 32) {
+    const int c = base + lane;
+    int32_t idx = -1;
+    float approx = -INFINITY;
+    if (c < total) {
+      idx = part_i[r * total + c];
+      approx = part_s[r * total + c];
+      if ((c % KP) == KP - 1 && idx >= 0) tau = fmaxf(tau, approx);   // a full list: something may have been dropped
+    }
+    double s = 0.0;
+    if (idx >= 0) {
+      const float* crow = catalog + int64_t(idx) * dim;
+      for (int d = 0; d < dim; ++d) s = fma(double(q[d]), double(crow[d]), s);   // the exact score definition
+    }
+    uint32_t cand = __ballot_sync(FULL, idx >= 0);
+    while (cand) {
+      const int src = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const double ss = __shfl_sync(FULL, s, src);
+      const int64_t ii = int64_t(__shfl_sync(FULL, idx, src)) + index_base;
+      const bool before = lane < k && r_before(ss, ii, mine.s, mine.i);
+      const uint32_t mask = __ballot_sync(FULL, before);
+      if (mask) {
+        const int pos = __ffs(mask) - 1;
+        const double up_s = __shfl_up_sync(FULL, mine.s, 1);
+        const int64_t up_i = __shfl_up_sync(FULL, (long long)mine.i, 1);
+        if (lane == pos) { mine.s = ss; mine.i = ii; }
+        else if (lane > pos) { mine.s = up_s; mine.i = up_i; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tau = fmaxf(tau, __shfl_xor_sync(FULL, tau, o));
+  if (lane < k) {
+    out_s[r * k + lane] = mine.s;
+    out_i[r * k + lane] = mine.i;
+  }
+  // guard: every dropped product has approx <= tau and |approx - exact| <= eps
+  const double kth_s = __shfl_sync(FULL, mine.s, k - 1);
+  const int64_t kth_i = __shfl_sync(FULL, (long long)mine.i, k - 1);
+  if (lane == 0) {
+    const double eps = ldexp(sqrt(qn) * double(max_norm), -16);
+    int bad = 0;
+    if (tau > -INFINITY) bad = (kth_i < 0) || !(kth_s - double(tau) > 2.0 * eps);
+    flags[r] = bad;
+  }
+}
+
+}  // namespace
+}  // namespace pc
+
+using namespace pc;
+
+extern "C" size_t pc_score_topk_workspace_bytes(int64_t rows, int units) {
+  if (rows <= 0 || units <= 0) return 0;
+  return size_t(rows) * size_t(units) * KP * (sizeof(float) + sizeof(int32_t));
+}
+
+extern "C" int pc_score_topk_dense(const float* q, int64_t rows, int dim, const float* catalog, int64_t products,
+                                   const int32_t* type_id, const int32_t* row_type, int k, int units, int64_t index_base,
+                                   float max_norm, double* out_scores, int64_t* out_idx, int32_t* flags, void* workspace,
+                                   size_t workspace_bytes, pc_stream_t stream) {
+  PC_REQUIRE(rows >= 0 && products >= 0, PC_ERR_INVALID, "score_topk_dense: negative size");
+  if (rows == 0) return PC_OK;
+  PC_REQUIRE(q && catalog && out_scores && out_idx && flags && workspace, PC_ERR_INVALID, "score_topk_dense: null pointer");
+  PC_REQUIRE(k >= 1 && k <= KP, PC_ERR_UNSUPPORTED, "score_topk_dense: k=%d outside [1,%d]", k, KP);
+  PC_REQUIRE(dim >= BK && dim % BK == 0 && dim <= 1024, PC_ERR_UNSUPPORTED, "score_topk_dense: dim=%d must be a multiple of %d", dim, BK);
+  PC_REQUIRE(products > 0 && products < (int64_t(1) << 31), PC_ERR_UNSUPPORTED, "score_topk_dense: catalog size out of range");
+  PC_REQUIRE(units >= 1 && units <= 4096, PC_ERR_INVALID, "score_topk_dense: bad units");
+  PC_REQUIRE(workspace_bytes >= pc_score_topk_workspace_bytes(rows, units), PC_ERR_WORKSPACE, "score_topk_dense: workspace too small");
+  PC_REQUIRE((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(catalog)) % 16 == 0, PC_ERR_INVALID, "score_topk_dense: 16-byte alignment (TMA)");
+  ScoreParams p;
+  p.rows = rows; p.products = products; p.k_blocks = dim / BK;
+  p.n_tiles = (products + SC_BN - 1) / SC_BN;
+  p.units_per_block = units;
+  p.tiles_per_unit = (p.n_tiles + units - 1) / units;
+  p.type_id = type_id; p.row_type = row_type;
+  p.part_s = reinterpret_cast<float*>(workspace);
+  p.part_i = reinterpret_cast<int32_t*>(p.part_s + size_t(rows) * units * KP);
+  CUtensorMap map_q, map_c;
+  if (int rc = make_map(&map_q, q, rows, dim, dim, BM)) return rc;
+  if (int rc = make_map(&map_c, catalog, products, dim, dim, SC_BN, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return rc;
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA(cudaFuncSetAttribute(score_topk_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+    configured = true;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int64_t total_units = ((rows + BM - 1) / BM) * units;
+  const int grid = int(total_units < sm_count() ? total_units : sm_count());
+  score_topk_tf32x3_kernel<<<grid, SC_THREADS, SC_SMEM, st>>>(map_q, map_c, p);
+  PC_LAUNCH_CHECK();
+  rescore_topk_kernel<<<unsigned(ceil_div(rows, 8)), 256, 0, st>>>(q, catalog, dim, rows, units, p.part_s, p.part_i, k,
+                                                                  index_base, max_norm, out_scores, out_idx, flags);
+  PC_LAUNCH_CHECK();
+  return PC_OK;
+}

@@ -493,6 +493,30 @@ def topk_segments(q: torch.Tensor, catalog: torch.Tensor, seg_begin: torch.Tenso
     return out_s, out_i
 
 
+def score_topk_dense(q: torch.Tensor, catalog: torch.Tensor, k: int, type_id: Optional[torch.Tensor] = None,
+                     row_type: Optional[torch.Tensor] = None, index_base: int = 0, max_norm: Optional[float] = None,
+                     units: Optional[int] = None):
+    """Dense tensor-core scoring + mask + top-k (pc_score_topk_dense).  Returns (scores f64 [R,k], idx i64 [R,k],
+    flags i32 [R]); flagged rows must be re-run on the exact path (topk_segments)."""
+    q = q.contiguous()
+    rows, dim = q.shape
+    if max_norm is None:
+        max_norm = float(catalog.norm(dim=1).max().item())
+    if units is None:
+        m_blocks = (rows + 127) // 128
+        n_tiles = (catalog.shape[0] + 127) // 128
+        units = max(1, min((2 * 148 + m_blocks - 1) // m_blocks, n_tiles, 4096))
+    out_s = torch.empty(rows, k, dtype=F64, device=q.device)
+    out_i = torch.empty(rows, k, dtype=I64, device=q.device)
+    flags = torch.empty(rows, dtype=I32, device=q.device)
+    ws = _lib.workspace(_lib.LIB.pc_score_topk_workspace_bytes(rows, units), q.device)
+    call("pc_score_topk_dense", dev(q, F32, "q"), rows, dim, dev(catalog, F32, "catalog"), catalog.shape[0],
+         dev(type_id, I32, "type_id"), dev(row_type, I32, "row_type"), k, units, int(index_base), float(max_norm),
+         dev(out_s, F64, "out_scores"), dev(out_i, I64, "out_idx"), dev(flags, I32, "flags"), dev(ws, torch.uint8, "ws"),
+         ws.numel(), stream())
+    return out_s, out_i, flags
+
+
 def topk_rows(values: torch.Tensor, k: int, splits: Optional[int] = None):
     """Row-wise top-k of a materialised fp32 matrix, ties -> lowest index (torch.topk replacement)."""
     values = values.contiguous()

@@ -81,6 +81,7 @@ class CatalogIndex:
         self.type_id = None
         self.members = None
         self.offsets = None
+        self._max_norm = None
         if type_id is not None:
             self.type_id = type_id.to(catalog.device, torch.int32).contiguous()
             n_types = int(num_types) if num_types is not None else (int(self.type_id.max().item()) + 1 if self.num_products else 0)
@@ -108,6 +109,21 @@ class CatalogIndex:
         beg = torch.where(valid, self.offsets[t], torch.zeros_like(t))
         end = torch.where(valid, self.offsets[t + 1], torch.zeros_like(t))
         return ops.topk_segments(queries, self.catalog, beg, end, k, self.members, self.index_base, splits)
+
+    def topk_dense(self, queries: torch.Tensor, k: int, row_type: Optional[torch.Tensor] = None):
+        """Same result as ``topk`` through the dense tensor-core path (BASELINE north_star part 4): 3xTF32 scoring
+        GEMM over the whole catalog, per-type mask and candidate selection in the epilogue, exact fp64 re-scoring.
+        Rows whose guard band fails are re-run on the exact segmented kernel, so the output is always exact."""
+        queries = queries.contiguous().float()
+        if self._max_norm is None:
+            self._max_norm = float(self.catalog.norm(dim=1).max().item())
+        rt = None if row_type is None else row_type.to(queries.device, torch.int32).contiguous()
+        s, i, flags = ops.score_topk_dense(queries, self.catalog, k, self.type_id, rt, self.index_base, self._max_norm)
+        bad = torch.nonzero(flags).squeeze(1)
+        if bad.numel():
+            fs, fi = self.topk(queries[bad], k, None if rt is None else rt[bad])
+            s[bad], i[bad] = fs, fi
+        return s, i
 
     def recommend(self, projected_embeddings: torch.Tensor, complementary_types: torch.Tensor, k: int = 10):
         """The loop of inference.py:93-113 for a whole batch: projected [B, Kt, D], types [B, Kt] ->

@@ -577,3 +577,34 @@ def test_indexed_triplet_loss_equals_gathered_loss_and_is_deterministic():
     t3 = table.clone().requires_grad_(True)
     ops.triplet_hinge_indexed(t3, ai, pi, ni, 1.0).backward()
     assert torch.equal(t3.grad, t1.grad)                                       # no atomics: bit-reproducible
+
+
+def test_dense_tensor_core_retrieval_equals_exact_segmented_path():
+    """north_star part 4 as worded: tcgen05 scoring GEMM + per-type mask + top-K over the whole catalog, then exact
+    fp64 re-scoring.  Must agree bit for bit (indices and scores) with the exact type-segmented kernel, including
+    rows whose guard band fails (many exact duplicates) and unmasked rows."""
+    from pcompanion_b200 import CatalogIndex, ops
+    from oracle import retrieval as oret
+    rng = np.random.default_rng(12)
+    p, t, r, k = 70_001, 37, 300, 10
+    cat = rng.normal(size=(p, 128)).astype(np.float32)
+    cat[rng.integers(0, p, 400)] = cat[123]                            # 400 exact duplicates -> ties and guard failures
+    tid = rng.integers(0, t, p).astype(np.int32)
+    q = rng.normal(size=(r, 128)).astype(np.float32)
+    q[:8] = cat[123] * 0.7                                             # rows whose best products are the duplicates
+    rt = rng.integers(0, t, r).astype(np.int32)
+    rt[:4] = tid[123]
+    index = CatalogIndex(torch.tensor(cat, device=dev()), torch.tensor(tid, device=dev()), num_types=t)
+    qt, rtt = torch.tensor(q, device=dev()), torch.tensor(rt, device=dev())
+    es, ei = index.topk(qt, k, rtt)
+    ds, di = index.topk_dense(qt, k, rtt)
+    assert torch.equal(di, ei) and torch.equal(ds, es)
+    os_, oi = oret.masked_topk(q[:16], cat, k, rt[:16], tid)
+    assert np.array_equal(di[:16].cpu().numpy(), oi) and np.array_equal(ds[:16].cpu().numpy(), os_)
+    # unmasked: every row ranks the whole catalog (metrics.py-style scoring)
+    eu = index.topk(qt[:130], k)
+    du = index.topk_dense(qt[:130], k)
+    assert torch.equal(du[1], eu[1]) and torch.equal(du[0], eu[0])
+    # the raw kernel flags exactly the rows it cannot prove, and proves the generic ones
+    _, _, flags = ops.score_topk_dense(qt, index.catalog, k, index.type_id, rtt, 0, None)
+    assert int(flags[8:].sum()) == 0 and int(flags[:4].sum()) >= 1
