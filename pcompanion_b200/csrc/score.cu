@@ -37,8 +37,9 @@ constexpr int SC_OFF_B = SC_OFF_LO + SC_LO_STAGES * SC_A_BYTES;
 constexpr int SC_OPERAND_BYTES = SC_OFF_B + SC_B_STAGES * 2 * SC_B_BYTES;   // 64 + 32 + 96 = 192 KB
 constexpr int SC_THREADS = 512;
 constexpr int SC_SPLIT_THREADS = 256;
-constexpr int SC_SMEM = SC_OPERAND_BYTES + 1024 + 4096;
 constexpr int KP = 16;                  // candidates kept per (row, unit)
+constexpr int SC_LIST_BYTES = BM * KP * 8;   // per-row candidate lists (score, index) of the 128 epilogue threads
+constexpr int SC_SMEM = SC_OPERAND_BYTES + SC_LIST_BYTES + 1024 + 4096;
 
 struct ScoreParams {
   int64_t rows, products;
@@ -57,7 +58,9 @@ score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                          const ScoreParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* misc = smem + SC_OPERAND_BYTES;
+  float* list_s = reinterpret_cast<float*>(smem + SC_OPERAND_BYTES);                 // [128][KP] scores
+  int32_t* list_i = reinterpret_cast<int32_t*>(smem + SC_OPERAND_BYTES + BM * KP * 4);   // [128][KP] indices
+  uint8_t* misc = smem + SC_OPERAND_BYTES + SC_LIST_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
   int32_t* types_s = reinterpret_cast<int32_t*>(misc + 512);   // [2][128] product types of the tile in flight
@@ -221,11 +224,15 @@ score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       }
     })
   } else if (warp >= 4) {
-    // ---------------- epilogue: thread = one score row; sorted candidate list (score desc, index asc) in registers
+    // ---------------- epilogue: thread = one score row.  Its sorted candidate list (score desc, index asc) lives in
+    // shared memory; only the admission threshold (weakest kept score) stays in a register, so the common case
+    // (product masked out or below the threshold) is a couple of instructions per score.
     int acc = 0;
     uint32_t acc_phase = 0;
     const int quad = warp - 4;
     const int trow = quad * 32 + lane;
+    float* my_s = list_s + trow * KP;
+    int32_t* my_i = list_i + trow * KP;
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
       const int m0 = int((u / p.units_per_block) * BM);
       const int range = int(u % p.units_per_block);
@@ -234,18 +241,19 @@ score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       const int64_t row = int64_t(m0) + trow;
       const bool row_ok = row < p.rows;
       const int rt = (p.row_type && row_ok) ? p.row_type[row] : -1;
-      float cs[KP];
-      int32_t ci[KP];
-#pragma unroll
-      for (int j = 0; j < KP; ++j) { cs[j] = -INFINITY; ci[j] = -1; }
+      for (int j = 0; j < KP; ++j) { my_s[j] = -INFINITY; my_i[j] = -1; }
+      float thr = -INFINITY;          // score of the weakest kept candidate (list full) or -inf
+      int kept = 0;
+      auto type_of = [&](int64_t tile) -> int {
+        const int64_t pidx = tile * SC_BN + trow;
+        return (tile < t_end && pidx < p.products) ? (p.type_id ? p.type_id[pidx] : 0) : -2;   // -2: past the catalog end
+      };
+      int t_next = type_of(t_beg);
       for (int64_t nt = t_beg; nt < t_end; ++nt) {
         const int64_t n0 = nt * SC_BN;
-        // stage the tile's product types (-2 = past the end of the catalog)
         int32_t* ts = types_s + (acc & 1) * SC_BN;
-        {
-          const int64_t pidx = n0 + trow;
-          ts[trow] = pidx < p.products ? (p.type_id ? p.type_id[pidx] : 0) : -2;
-        }
+        ts[trow] = t_next;
+        t_next = type_of(nt + 1);      // in flight while this tile is processed
         asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(tfull_bar + 8 * acc, acc_phase);
         tc_fence_after();
@@ -254,25 +262,21 @@ score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
           tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * SC_BN + c0), r);
           tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * SC_BN + SC_BN + c0), rc);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 32; ++j) {   // fully unrolled: r[] / rc[] must stay in registers
             const int t = ts[c0 + j];
-            const bool eligible = row_ok && t != -2 && (rt < 0 || t == rt);
             const float y = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
-            const int32_t idx = int32_t(n0 + c0 + j);
-            if (eligible && (y > cs[KP - 1] || (y == cs[KP - 1] && ci[KP - 1] < 0))) {
-              // insert keeping (score desc, index asc); indices arrive ascending, so equal scores go after
-              float vs = y;
-              int32_t vi = idx;
-              bool shifting = false;
-#pragma unroll
-              for (int q = 0; q < KP; ++q) {
-                if (shifting || vs > cs[q] || ci[q] < 0) {   // first strictly smaller (or empty) slot, then shift the tail
-                  const float tsv = cs[q]; const int32_t tiv = ci[q];
-                  cs[q] = vs; ci[q] = vi;
-                  vs = tsv; vi = tiv;
-                  shifting = true;
-                }
+            if (row_ok && t != -2 && (rt < 0 || t == rt) && (kept < KP || y > thr)) {
+              // insert keeping (score desc, index asc): indices arrive ascending, so an equal score goes after
+              int pos = kept < KP ? kept : KP - 1;
+              while (pos > 0 && my_s[pos - 1] < y) {
+                my_s[pos] = my_s[pos - 1];
+                my_i[pos] = my_i[pos - 1];
+                --pos;
               }
+              my_s[pos] = y;
+              my_i[pos] = int32_t(n0 + c0 + j);
+              if (kept < KP) ++kept;
+              if (kept == KP) thr = my_s[KP - 1];
             }
           }
         }
@@ -283,11 +287,10 @@ score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
           acc_phase ^= 1;
         }
       }
-      if (row < p.rows) {
+      if (row_ok) {
         float* os = p.part_s + (row * p.units_per_block + range) * KP;
         int32_t* oi = p.part_i + (row * p.units_per_block + range) * KP;
-#pragma unroll
-        for (int j = 0; j < KP; ++j) { os[j] = cs[j]; oi[j] = ci[j]; }
+        for (int j = 0; j < KP; ++j) { os[j] = my_s[j]; oi[j] = my_i[j]; }
       }
     }
   }

@@ -588,8 +588,10 @@ def test_dense_tensor_core_retrieval_equals_exact_segmented_path():
     rng = np.random.default_rng(12)
     p, t, r, k = 70_001, 37, 300, 10
     cat = rng.normal(size=(p, 128)).astype(np.float32)
-    cat[rng.integers(0, p, 400)] = cat[123]                            # 400 exact duplicates -> ties and guard failures
+    cat[rng.integers(0, p, 400)] = cat[123]                            # 400 exact duplicates -> ties
     tid = rng.integers(0, t, p).astype(np.int32)
+    cat[1000:1040] = cat[123]                                          # 40 adjacent duplicates of one type: more equal
+    tid[1000:1040] = tid[123]                                          # top scores than one candidate list holds
     q = rng.normal(size=(r, 128)).astype(np.float32)
     q[:8] = cat[123] * 0.7                                             # rows whose best products are the duplicates
     rt = rng.integers(0, t, r).astype(np.int32)
