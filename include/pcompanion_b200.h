@@ -192,12 +192,12 @@ int pc_topk_groups(const float* q, int64_t rows, int dim, const float* catalog, 
                    const int32_t* row_ids, const int32_t* grp_begin, const int64_t* seg_begin, const int64_t* seg_end,
                    int64_t n_groups, int k, int splits, int64_t index_base, double* out_scores, int64_t* out_idx,
                    void* workspace, size_t workspace_bytes, pc_stream_t stream);
-/* Dense whole-catalog variant on the tensor cores (north_star part 4): scores = Q . C^T as a 3xTF32 tcgen05
- * GEMM (never materialised), per-type mask (type_id[p] == row_type[r]; row_type NULL or < 0 = no mask) and a
+/* Dense whole-catalog variant on the tensor cores (north_star part 4): scores = Q . C^T as a TF32 tcgen05
+ * GEMM (never materialised; approximate scores only select candidates), per-type mask (type_id[p] == row_type[r]; row_type NULL or < 0 = no mask) and a
  * per-row candidate list fused into the epilogue, then exact float64 re-scoring + ranking of the candidates.
  * `units` = product ranges per 128-row block (parallelism).  flags[r] = 1 when the guard band cannot prove
  * that no dropped product belongs to the top-k (the caller re-runs such rows on pc_topk_groups); results of
- * unflagged rows are identical to pc_topk_groups.  k <= 16, dim % 32 == 0. */
+ * unflagged rows are identical to pc_topk_groups.  k <= 16, dim % 32 == 0, dim <= 128. */
 size_t pc_score_topk_workspace_bytes(int64_t rows, int units);
 int pc_score_topk_dense(const float* q, int64_t rows, int dim, const float* catalog, int64_t products,
                         const int32_t* type_id, const int32_t* row_type, int k, int units, int64_t index_base,

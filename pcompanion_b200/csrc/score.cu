@@ -9,17 +9,18 @@
 // is restricted to one type, the type-segmented kernel in retrieval.cu does 1/#types of the work and
 // is the default; see DESIGN.md.)
 //
-// Kernel 1 (score_topk_tf32x3_kernel): 128 score rows x 128 products per tile, 3xTF32 tcgen05.mma
-// (fp32-faithful scores, same operand split / two-accumulator scheme as gemm.cu).  A CTA owns one
-// 128-row block and a contiguous range of product tiles ("unit"), so each epilogue thread (= one score
-// row) keeps its own sorted list of the best KP candidates in registers across the whole range; masked
-// products (type_id[p] != row_type[r]) never enter it.  Per unit it writes KP (approx score, index)
-// candidates per row.
+// Kernel 1 (score_topk_tf32_kernel): 128 score rows x 128 products per tile, single-pass TF32 tcgen05.mma.
+// The approximate scores only have to find CANDIDATES - exactness comes from kernel 2 - so there is no
+// operand split: TMA lands fp32 tiles in shared memory and the tensor core reads them directly (it ignores
+// the low 13 mantissa bits).  A CTA owns one 128-row block (its query tile stays resident in shared memory)
+// and a contiguous range of product tiles ("unit") streamed through an 8-deep TMA ring; each epilogue thread
+// (= one score row) keeps a sorted list of the best KP candidates across the whole range; masked products
+// (type_id[p] != row_type[r]) never enter it.  Accumulators are quadruple-buffered in TMEM.
 // Kernel 2 (rescore_topk_kernel): one warp per row re-scores the candidates exactly (float64, sequential
 // over d - the score definition of retrieval.cu / oracle/retrieval.py), ranks them (score desc, index
 // asc) and checks the guard band: every product dropped by kernel 1 had an approximate score <= tau (the
-// weakest kept candidate of a full list); if the exact K-th score is not above tau + eps (eps bounds the
-// 3xTF32 error via |q| * max|c|), the row is flagged and the host re-runs it on the exact path.
+// weakest kept candidate of a full list); if the exact K-th score is not above tau + 2 eps (eps = worst-case
+// TF32 truncation error 2^-9 |q| max|c|), the row is flagged and the host re-runs it on the exact path.
 #include <math.h>
 
 #include "common.cuh"
@@ -29,16 +30,15 @@ namespace pc {
 namespace {
 
 constexpr int SC_BN = 128;              // products per tile
-constexpr int SC_A_BYTES = BM * BK * 4;
-constexpr int SC_B_BYTES = SC_BN * BK * 4;
-constexpr int SC_A_STAGES = 4, SC_LO_STAGES = 2, SC_B_STAGES = 3;
-constexpr int SC_OFF_LO = SC_A_STAGES * SC_A_BYTES;
-constexpr int SC_OFF_B = SC_OFF_LO + SC_LO_STAGES * SC_A_BYTES;
-constexpr int SC_OPERAND_BYTES = SC_OFF_B + SC_B_STAGES * 2 * SC_B_BYTES;   // 64 + 32 + 96 = 192 KB
-constexpr int SC_THREADS = 512;
-constexpr int SC_SPLIT_THREADS = 256;
-constexpr int KP = 16;                  // candidates kept per (row, unit)
-constexpr int SC_LIST_BYTES = BM * KP * 8;   // per-row candidate lists (score, index) of the 128 epilogue threads
+constexpr int SC_TILE_BYTES = BM * BK * 4;          // one K block of a 128-row operand tile: 16 KB
+constexpr int SC_MAX_KB = 4;                        // dim <= 128
+constexpr int SC_B_STAGES = 8;
+constexpr int SC_OFF_B = SC_MAX_KB * SC_TILE_BYTES; // resident query tile first: 64 KB
+constexpr int SC_OPERAND_BYTES = SC_OFF_B + SC_B_STAGES * SC_TILE_BYTES;   // + 128 KB product ring = 192 KB
+constexpr int SC_THREADS = 256;
+constexpr int SC_ACC = 4;                           // TMEM accumulator buffers (4 x 128 columns)
+constexpr int KP = 16;                              // candidates kept per (row, unit)
+constexpr int SC_LIST_BYTES = BM * KP * 8;          // per-row candidate lists (score, index) of the 128 epilogue threads
 constexpr int SC_SMEM = SC_OPERAND_BYTES + SC_LIST_BYTES + 1024 + 4096;
 
 struct ScoreParams {
@@ -54,35 +54,29 @@ struct ScoreParams {
 };
 
 __global__ void __launch_bounds__(SC_THREADS, 1)
-score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
-                         const ScoreParams p) {
+score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
+                       const ScoreParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* list_s = reinterpret_cast<float*>(smem + SC_OPERAND_BYTES);                 // [128][KP] scores
+  float* list_s = reinterpret_cast<float*>(smem + SC_OPERAND_BYTES);                     // [128][KP] scores
   int32_t* list_i = reinterpret_cast<int32_t*>(smem + SC_OPERAND_BYTES + BM * KP * 4);   // [128][KP] indices
   uint8_t* misc = smem + SC_OPERAND_BYTES + SC_LIST_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // q_full, q_empty, b_full[8], b_empty[8], tfull[4], tempty[4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
   int32_t* types_s = reinterpret_cast<int32_t*>(misc + 512);   // [2][128] product types of the tile in flight
-  const uint32_t a_full = smem_u32(bars + 0), a_ready = smem_u32(bars + SC_A_STAGES), a_empty = smem_u32(bars + 2 * SC_A_STAGES);
-  const uint32_t lo_empty = smem_u32(bars + 3 * SC_A_STAGES), b_full = lo_empty + 8 * SC_LO_STAGES;
-  const uint32_t b_ready = b_full + 8 * SC_B_STAGES, b_empty = b_ready + 8 * SC_B_STAGES;
-  const uint32_t tfull_bar = b_empty + 8 * SC_B_STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t q_full = smem_u32(bars + 0), q_empty = smem_u32(bars + 1);
+  const uint32_t b_full = smem_u32(bars + 2), b_empty = b_full + 8 * SC_B_STAGES;
+  const uint32_t tfull_bar = b_empty + 8 * SC_B_STAGES, tempty_bar = tfull_bar + 8 * SC_ACC;
   const int warp = warp_id(), lane = lane_id();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SC_A_STAGES; ++s) {
-      mbar_init(a_full + 8 * s, 1);
-      mbar_init(a_ready + 8 * s, SC_SPLIT_THREADS / 32);
-      mbar_init(a_empty + 8 * s, 1);
-    }
-    for (int s = 0; s < SC_LO_STAGES; ++s) mbar_init(lo_empty + 8 * s, 1);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < SC_B_STAGES; ++s) {
       mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_ready + 8 * s, SC_SPLIT_THREADS / 32);
       mbar_init(b_empty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < SC_ACC; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
       mbar_init(tempty_bar + 8 * s, 128);
     }
@@ -100,139 +94,76 @@ score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   const int64_t m_blocks = (p.rows + BM - 1) / BM;
   const int64_t units = m_blocks * p.units_per_block;
   // unit u -> 128-row block u / S, product tiles [ (u % S) * tpu, min(n_tiles, (u % S + 1) * tpu) )
-#define SC_FOR_EACH_TILE(...)                                                               \
-  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {                                 \
-    const int m0 = int((u / p.units_per_block) * BM);                                       \
-    const int range = int(u % p.units_per_block);                                           \
-    const int64_t t_beg = int64_t(range) * p.tiles_per_unit;                                \
-    const int64_t t_end = t_beg + p.tiles_per_unit < p.n_tiles ? t_beg + p.tiles_per_unit : p.n_tiles; \
-    (void)m0;                                                                               \
-    for (int64_t nt = t_beg; nt < t_end; ++nt) {                                            \
-      __VA_ARGS__                                                                           \
-    }                                                                                       \
-  }
 
   if (warp == 0) {
-    if (lane == 0) {
-      Ring<SC_A_STAGES> ra;
-      SC_FOR_EACH_TILE({
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(a_empty + 8 * ra.stage, ra.phase ^ 1);
-          mbar_arrive_expect_tx(a_full + 8 * ra.stage, SC_A_BYTES);
-          tma_load_2d(smem_u32(smem + ra.stage * SC_A_BYTES), &map_q, kb * BK, m0, a_full + 8 * ra.stage);
-          ra.advance();
-        }
-      })
-    }
-  } else if (warp == 3) {
+    // ---------------- TMA producer: query tile once per unit, product tiles through the ring
     if (lane == 0) {
       Ring<SC_B_STAGES> rb;
-      SC_FOR_EACH_TILE({
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(b_empty + 8 * rb.stage, rb.phase ^ 1);
-          mbar_arrive_expect_tx(b_full + 8 * rb.stage, SC_B_BYTES);
-          tma_load_2d(smem_u32(smem + SC_OFF_B + rb.stage * 2 * SC_B_BYTES), &map_c, kb * BK, int(nt * SC_BN),
-                      b_full + 8 * rb.stage);
-          rb.advance();
+      uint32_t q_phase = 0;
+      for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int m0 = int((u / p.units_per_block) * BM);
+        const int64_t t_beg = (u % p.units_per_block) * p.tiles_per_unit;
+        const int64_t t_end = t_beg + p.tiles_per_unit < p.n_tiles ? t_beg + p.tiles_per_unit : p.n_tiles;
+        mbar_wait(q_empty, q_phase ^ 1);          // previous unit's MMAs no longer read the query tile
+        mbar_arrive_expect_tx(q_full, uint32_t(p.k_blocks) * SC_TILE_BYTES);
+        for (int kb = 0; kb < p.k_blocks; ++kb) tma_load_2d(smem_u32(smem + kb * SC_TILE_BYTES), &map_q, kb * BK, m0, q_full);
+        q_phase ^= 1;
+        for (int64_t nt = t_beg; nt < t_end; ++nt) {
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(b_empty + 8 * rb.stage, rb.phase ^ 1);
+            mbar_arrive_expect_tx(b_full + 8 * rb.stage, SC_TILE_BYTES);
+            tma_load_2d(smem_u32(smem + SC_OFF_B + rb.stage * SC_TILE_BYTES), &map_c, kb * BK, int(nt * SC_BN),
+                        b_full + 8 * rb.stage);
+            rb.advance();
+          }
         }
-      })
+      }
     }
   } else if (warp == 1) {
-    Ring<SC_A_STAGES> ra;
-    Ring<SC_LO_STAGES> rl;
+    // ---------------- MMA issuer: one tcgen05.mma kind::tf32 per 8 dims, operands straight from the TMA tiles
     Ring<SC_B_STAGES> rb;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    Ring<SC_ACC> ra;
+    uint32_t q_phase = 0;
     const uint32_t idesc = instr_desc_tf32(SC_BN);
-    SC_FOR_EACH_TILE({
-      mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_main = tmem_base + uint32_t(acc * 2 * SC_BN), d_cross = d_main + SC_BN;
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
-        mbar_wait(b_ready + 8 * rb.stage, rb.phase);
-        mbar_wait(a_ready + 8 * ra.stage, ra.phase);
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+      const int64_t t_beg = (u % p.units_per_block) * p.tiles_per_unit;
+      const int64_t t_end = t_beg + p.tiles_per_unit < p.n_tiles ? t_beg + p.tiles_per_unit : p.n_tiles;
+      mbar_wait(q_full, q_phase);
+      q_phase ^= 1;
+      for (int64_t nt = t_beg; nt < t_end; ++nt) {
+        mbar_wait(tempty_bar + 8 * ra.stage, ra.phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t base = smem_u32(smem);
-          const uint64_t a_hi = smem_desc_k_sw128(base + ra.stage * SC_A_BYTES);
-          const uint64_t a_lo = smem_desc_k_sw128(base + SC_OFF_LO + rl.stage * SC_A_BYTES);
-          const uint64_t b_hi = smem_desc_k_sw128(base + SC_OFF_B + rb.stage * 2 * SC_B_BYTES);
-          const uint64_t b_lo = smem_desc_k_sw128(base + SC_OFF_B + rb.stage * 2 * SC_B_BYTES + SC_B_BYTES);
+        const uint32_t d = tmem_base + uint32_t(ra.stage * SC_BN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(b_full + 8 * rb.stage, rb.phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t base = smem_u32(smem);
+            const uint64_t a_desc = smem_desc_k_sw128(base + kb * SC_TILE_BYTES);
+            const uint64_t b_desc = smem_desc_k_sw128(base + SC_OFF_B + rb.stage * SC_TILE_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t adv = uint64_t(kk * 32 >> 4);
-            umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | kk) != 0);
-            umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
+            for (int kk = 0; kk < BK / 8; ++kk) umma_tf32(d, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, (kb | kk) != 0);
+            umma_commit(b_empty + 8 * rb.stage);
+            if (kb == p.k_blocks - 1) umma_commit(tfull_bar + 8 * ra.stage);
           }
-          umma_commit(a_empty + 8 * ra.stage);
-          umma_commit(lo_empty + 8 * rl.stage);
-          umma_commit(b_empty + 8 * rb.stage);
-          if (kb == p.k_blocks - 1) umma_commit(tfull_bar + 8 * acc);
+          __syncwarp();
+          rb.advance();
         }
-        __syncwarp();
         ra.advance();
-        rl.advance();
-        rb.advance();
       }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    })
-  } else if (warp >= 8) {
-    // operand split: both tiles raw -> hi in place, lo next to it (queries and catalog are both activations here)
-    Ring<SC_A_STAGES> ra;
-    Ring<SC_LO_STAGES> rl;
-    Ring<SC_B_STAGES> rb;
-    const int tid = threadIdx.x - 256;
-    SC_FOR_EACH_TILE({
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
-        mbar_wait(b_full + 8 * rb.stage, rb.phase);
-        uint8_t* bh = smem + SC_OFF_B + rb.stage * 2 * SC_B_BYTES;
-#pragma unroll
-        for (int i = tid; i < SC_B_BYTES / 16; i += SC_SPLIT_THREADS) {
-          const float4 v = *reinterpret_cast<const float4*>(bh + i * 16);
-          float4 h, l;
-          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-          *reinterpret_cast<float4*>(bh + i * 16) = h;
-          *reinterpret_cast<float4*>(bh + SC_B_BYTES + i * 16) = l;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_ready + 8 * rb.stage);
-        rb.advance();
-        mbar_wait(a_full + 8 * ra.stage, ra.phase);
-        mbar_wait(lo_empty + 8 * rl.stage, rl.phase ^ 1);
-        uint8_t* ah = smem + ra.stage * SC_A_BYTES;
-        uint8_t* al = smem + SC_OFF_LO + rl.stage * SC_A_BYTES;
-#pragma unroll
-        for (int i = tid; i < SC_A_BYTES / 16; i += SC_SPLIT_THREADS) {
-          const float4 v = *reinterpret_cast<const float4*>(ah + i * 16);
-          float4 h, l;
-          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-          *reinterpret_cast<float4*>(ah + i * 16) = h;
-          *reinterpret_cast<float4*>(al + i * 16) = l;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready + 8 * ra.stage);
-        ra.advance();
-        rl.advance();
-      }
-    })
+      if (lane == 0) umma_commit(q_empty);
+      __syncwarp();
+    }
   } else if (warp >= 4) {
     // ---------------- epilogue: thread = one score row.  Its sorted candidate list (score desc, index asc) lives in
-    // shared memory; only the admission threshold (weakest kept score) stays in a register, so the common case
-    // (product masked out or below the threshold) is a couple of instructions per score.
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    // shared memory; only the admission threshold stays in a register.  Per 32-score chunk an eligibility bit mask is
+    // built first (type match, above threshold), so the common case costs a few instructions per score.
+    Ring<SC_ACC> ra;
     const int quad = warp - 4;
     const int trow = quad * 32 + lane;
     float* my_s = list_s + trow * KP;
     int32_t* my_i = list_i + trow * KP;
+    int parity = 0;
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
       const int m0 = int((u / p.units_per_block) * BM);
       const int range = int(u % p.units_per_block);
@@ -242,7 +173,7 @@ score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       const bool row_ok = row < p.rows;
       const int rt = (p.row_type && row_ok) ? p.row_type[row] : -1;
       for (int j = 0; j < KP; ++j) { my_s[j] = -INFINITY; my_i[j] = -1; }
-      float thr = -INFINITY;          // score of the weakest kept candidate (list full) or -inf
+      float thr = -INFINITY;          // weakest kept score once the list is full
       int kept = 0;
       auto type_of = [&](int64_t tile) -> int {
         const int64_t pidx = tile * SC_BN + trow;
@@ -251,41 +182,48 @@ score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       int t_next = type_of(t_beg);
       for (int64_t nt = t_beg; nt < t_end; ++nt) {
         const int64_t n0 = nt * SC_BN;
-        int32_t* ts = types_s + (acc & 1) * SC_BN;
+        int32_t* ts = types_s + parity * SC_BN;
+        parity ^= 1;
         ts[trow] = t_next;
         t_next = type_of(nt + 1);      // in flight while this tile is processed
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        mbar_wait(tfull_bar + 8 * ra.stage, ra.phase);
         tc_fence_after();
         for (int c0 = 0; c0 < SC_BN; c0 += 32) {
-          uint32_t r[32], rc[32];
-          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * SC_BN + c0), r);
-          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * SC_BN + SC_BN + c0), rc);
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(ra.stage * SC_BN + c0), r);
+          uint32_t mask = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {   // fully unrolled: r[] / rc[] must stay in registers
+          for (int j = 0; j < 32; ++j) {
             const int t = ts[c0 + j];
-            const float y = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
-            if (row_ok && t != -2 && (rt < 0 || t == rt) && (kept < KP || y > thr)) {
-              // insert keeping (score desc, index asc): indices arrive ascending, so an equal score goes after
-              int pos = kept < KP ? kept : KP - 1;
-              while (pos > 0 && my_s[pos - 1] < y) {
-                my_s[pos] = my_s[pos - 1];
-                my_i[pos] = my_i[pos - 1];
-                --pos;
+            const bool e = t != -2 && (rt < 0 || t == rt) && (kept < KP || __uint_as_float(r[j]) > thr);
+            mask |= uint32_t(e) << j;
+          }
+          if (row_ok && mask) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (mask & (1u << j)) {
+                const float y = __uint_as_float(r[j]);
+                if (kept < KP || y > my_s[KP - 1]) {   // the threshold may have moved inside this chunk
+                  // insert keeping (score desc, index asc): indices arrive ascending, so an equal score goes after
+                  int pos = kept < KP ? kept : KP - 1;
+                  while (pos > 0 && my_s[pos - 1] < y) {
+                    my_s[pos] = my_s[pos - 1];
+                    my_i[pos] = my_i[pos - 1];
+                    --pos;
+                  }
+                  my_s[pos] = y;
+                  my_i[pos] = int32_t(n0 + c0 + j);
+                  if (kept < KP) ++kept;
+                  if (kept == KP) thr = my_s[KP - 1];
+                }
               }
-              my_s[pos] = y;
-              my_i[pos] = int32_t(n0 + c0 + j);
-              if (kept < KP) ++kept;
-              if (kept == KP) thr = my_s[KP - 1];
             }
           }
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar + 8 * acc);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
+        mbar_arrive(tempty_bar + 8 * ra.stage);
+        ra.advance();
       }
       if (row_ok) {
         float* os = p.part_s + (row * p.units_per_block + range) * KP;
@@ -294,7 +232,6 @@ score_topk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       }
     }
   }
-#undef SC_FOR_EACH_TILE
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -370,7 +307,7 @@ rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ catal
   const double kth_s = __shfl_sync(FULL, mine.s, k - 1);
   const int64_t kth_i = __shfl_sync(FULL, (long long)mine.i, k - 1);
   if (lane == 0) {
-    const double eps = ldexp(sqrt(qn) * double(max_norm), -16);
+    const double eps = ldexp(sqrt(qn) * double(max_norm), -9);   // worst-case TF32 truncation of both operands
     int bad = 0;
     if (tau > -INFINITY) bad = (kth_i < 0) || !(kth_s - double(tau) > 2.0 * eps);
     flags[r] = bad;
@@ -395,7 +332,7 @@ extern "C" int pc_score_topk_dense(const float* q, int64_t rows, int dim, const 
   if (rows == 0) return PC_OK;
   PC_REQUIRE(q && catalog && out_scores && out_idx && flags && workspace, PC_ERR_INVALID, "score_topk_dense: null pointer");
   PC_REQUIRE(k >= 1 && k <= KP, PC_ERR_UNSUPPORTED, "score_topk_dense: k=%d outside [1,%d]", k, KP);
-  PC_REQUIRE(dim >= BK && dim % BK == 0 && dim <= 1024, PC_ERR_UNSUPPORTED, "score_topk_dense: dim=%d must be a multiple of %d", dim, BK);
+  PC_REQUIRE(dim >= BK && dim % BK == 0 && dim <= BK * SC_MAX_KB, PC_ERR_UNSUPPORTED, "score_topk_dense: dim=%d must be a multiple of %d up to %d", dim, BK, BK * SC_MAX_KB);
   PC_REQUIRE(products > 0 && products < (int64_t(1) << 31), PC_ERR_UNSUPPORTED, "score_topk_dense: catalog size out of range");
   PC_REQUIRE(units >= 1 && units <= 4096, PC_ERR_INVALID, "score_topk_dense: bad units");
   PC_REQUIRE(workspace_bytes >= pc_score_topk_workspace_bytes(rows, units), PC_ERR_WORKSPACE, "score_topk_dense: workspace too small");
@@ -413,13 +350,13 @@ extern "C" int pc_score_topk_dense(const float* q, int64_t rows, int dim, const 
   if (int rc = make_map(&map_c, catalog, products, dim, dim, SC_BN, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return rc;
   static bool configured = false;
   if (!configured) {
-    PC_CUDA(cudaFuncSetAttribute(score_topk_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+    PC_CUDA(cudaFuncSetAttribute(score_topk_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
     configured = true;
   }
   cudaStream_t st = as_stream(stream);
   const int64_t total_units = ((rows + BM - 1) / BM) * units;
   const int grid = int(total_units < sm_count() ? total_units : sm_count());
-  score_topk_tf32x3_kernel<<<grid, SC_THREADS, SC_SMEM, st>>>(map_q, map_c, p);
+  score_topk_tf32_kernel<<<grid, SC_THREADS, SC_SMEM, st>>>(map_q, map_c, p);
   PC_LAUNCH_CHECK();
   rescore_topk_kernel<<<unsigned(ceil_div(rows, 8)), 256, 0, st>>>(q, catalog, dim, rows, units, p.part_s, p.part_i, k,
                                                                   index_base, max_norm, out_scores, out_idx, flags);
