@@ -93,7 +93,8 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 
   const int64_t m_blocks = (p.rows + BM - 1) / BM;
   const int64_t units = m_blocks * p.units_per_block;
-  // unit u -> 128-row block u / S, product tiles [ (u % S) * tpu, min(n_tiles, (u % S + 1) * tpu) )
+  // unit u -> 128-row block u % m_blocks, product range u / m_blocks: CTAs that run at the same time sweep the same
+  // product range for different row blocks, so the catalog tiles are shared through L2
 
   if (warp == 0) {
     // ---------------- TMA producer: query tile once per unit, product tiles through the ring
@@ -101,8 +102,8 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       Ring<SC_B_STAGES> rb;
       uint32_t q_phase = 0;
       for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const int m0 = int((u / p.units_per_block) * BM);
-        const int64_t t_beg = (u % p.units_per_block) * p.tiles_per_unit;
+        const int m0 = int((u % m_blocks) * BM);
+        const int64_t t_beg = (u / m_blocks) * p.tiles_per_unit;
         const int64_t t_end = t_beg + p.tiles_per_unit < p.n_tiles ? t_beg + p.tiles_per_unit : p.n_tiles;
         mbar_wait(q_empty, q_phase ^ 1);          // previous unit's MMAs no longer read the query tile
         mbar_arrive_expect_tx(q_full, uint32_t(p.k_blocks) * SC_TILE_BYTES);
@@ -126,7 +127,7 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint32_t q_phase = 0;
     const uint32_t idesc = instr_desc_tf32(SC_BN);
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-      const int64_t t_beg = (u % p.units_per_block) * p.tiles_per_unit;
+      const int64_t t_beg = (u / m_blocks) * p.tiles_per_unit;
       const int64_t t_end = t_beg + p.tiles_per_unit < p.n_tiles ? t_beg + p.tiles_per_unit : p.n_tiles;
       mbar_wait(q_full, q_phase);
       q_phase ^= 1;
@@ -165,8 +166,8 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     int32_t* my_i = list_i + trow * KP;
     int parity = 0;
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-      const int m0 = int((u / p.units_per_block) * BM);
-      const int range = int(u % p.units_per_block);
+      const int m0 = int((u % m_blocks) * BM);
+      const int range = int(u / m_blocks);
       const int64_t t_beg = int64_t(range) * p.tiles_per_unit;
       const int64_t t_end = t_beg + p.tiles_per_unit < p.n_tiles ? t_beg + p.tiles_per_unit : p.n_tiles;
       const int64_t row = int64_t(m0) + trow;

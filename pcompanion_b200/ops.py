@@ -505,6 +505,8 @@ def score_topk_dense(q: torch.Tensor, catalog: torch.Tensor, k: int, type_id: Op
     if units is None:
         m_blocks = (rows + 127) // 128
         n_tiles = (catalog.shape[0] + 127) // 128
+        # a unit is (128-row block, product range); ~2 units per SM.  More, smaller units balance better but every
+        # unit adds KP candidates per row to the exact re-scoring pass (measured: 20 units/SM is 30 % slower)
         units = max(1, min((2 * 148 + m_blocks - 1) // m_blocks, n_tiles, 4096))
     out_s = torch.empty(rows, k, dtype=F64, device=q.device)
     out_i = torch.empty(rows, k, dtype=I64, device=q.device)
