@@ -217,14 +217,14 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       for (int kb = 0; kb < k_blocks; ++kb) {
         if (p.bsplit) {   // weight tile: hi in place, lo right behind it
           mbar_wait(b_full + 8 * rb.stage, rb.phase);
-          uint8_t* bh = smem + OFF_B + rb.stage * 2 * B_BYTES;
+          const uint32_t bh = smem_u32(smem + OFF_B + rb.stage * 2 * B_BYTES);
           for (int i = tid; i < int(b_tile_bytes / 16); i += SPLIT_THREADS) {
-            const float4 v = *reinterpret_cast<const float4*>(bh + i * 16);
+            const float4 v = lds128(bh + i * 16);
             float4 h, l;
             h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
             l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-            *reinterpret_cast<float4*>(bh + i * 16) = h;
-            *reinterpret_cast<float4*>(bh + B_BYTES + i * 16) = l;
+            sts128(bh + i * 16, h);
+            sts128(bh + B_BYTES + i * 16, l);
           }
           fence_proxy_async();
           __syncwarp();
@@ -233,16 +233,18 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
         mbar_wait(a_full + 8 * ra.stage, ra.phase);
         mbar_wait(lo_empty + 8 * rl.stage, rl.phase ^ 1);
-        uint8_t* hi_base = smem + ra.stage * A_BYTES;
-        uint8_t* lo_base = smem + OFF_LO + rl.stage * A_BYTES;
+        const uint32_t hi_base = smem_u32(smem + ra.stage * A_BYTES);
+        const uint32_t lo_base = smem_u32(smem + OFF_LO + rl.stage * A_BYTES);
+        float4 v[A_BYTES / 16 / SPLIT_THREADS];
 #pragma unroll
-        for (int i = tid; i < A_BYTES / 16; i += SPLIT_THREADS) {
-          const float4 v = *reinterpret_cast<const float4*>(hi_base + i * 16);
+        for (int it = 0; it < A_BYTES / 16 / SPLIT_THREADS; ++it) v[it] = lds128(hi_base + (tid + it * SPLIT_THREADS) * 16);
+#pragma unroll
+        for (int it = 0; it < A_BYTES / 16 / SPLIT_THREADS; ++it) {
           float4 h, l;
-          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-          *reinterpret_cast<float4*>(hi_base + i * 16) = h;
-          *reinterpret_cast<float4*>(lo_base + i * 16) = l;
+          h.x = to_tf32(v[it].x); h.y = to_tf32(v[it].y); h.z = to_tf32(v[it].z); h.w = to_tf32(v[it].w);
+          l.x = to_tf32(v[it].x - h.x); l.y = to_tf32(v[it].y - h.y); l.z = to_tf32(v[it].z - h.z); l.w = to_tf32(v[it].w - h.w);
+          sts128(hi_base + (tid + it * SPLIT_THREADS) * 16, h);
+          sts128(lo_base + (tid + it * SPLIT_THREADS) * 16, l);
         }
         fence_proxy_async();
         __syncwarp();
@@ -258,6 +260,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int quad = warp - 4;
     const int trow = quad * 32 + lane;                      // row of the tile this thread owns
     const bool issuer = threadIdx.x == 128;                 // first epilogue thread issues the bulk stores
+    const uint32_t bias_addr = smem_u32(bias_s), out_addr = smem_u32(out_tile);
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       const int m0 = int((t / p.n_tiles) * BM);
       const int64_t row = int64_t(m0) + trow;
@@ -273,7 +276,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int n = n0 + c0;
         float y[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]) + bias_s[n + j];
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = lds128(bias_addr + (n + j) * 4);
+          y[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]) + b4.x;
+          y[j + 1] = __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]) + b4.y;
+          y[j + 2] = __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]) + b4.z;
+          y[j + 3] = __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]) + b4.w;
+        }
         if (p.epilogue == EPI_BIAS_TANH) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = tanhf(y[j]);
@@ -296,8 +305,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 8; ++j)   // 128-byte swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
-          *reinterpret_cast<float4*>(out_tile + trow * 128 + ((j ^ (trow & 7)) << 4)) =
-              make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          sts128(out_addr + trow * 128 + ((j ^ (trow & 7)) << 4), make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]));
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (issuer) {
@@ -480,19 +488,18 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
       mbar_wait(full_bar + 8 * pipe.stage, pipe.phase);
       mbar_wait(lo_empty_bar + 8 * lo.stage, lo.phase ^ 1);
       if (active) {
-        uint8_t* base = smem + pipe.stage * WG_STAGE_BYTES + op_off;
-        uint8_t* lo_base = smem + WG_OFF_LO + lo.stage * WG_STAGE_BYTES + op_off;
+        const uint32_t base = smem_u32(smem + pipe.stage * WG_STAGE_BYTES + op_off);
+        const uint32_t lo_base = smem_u32(smem + WG_OFF_LO + lo.stage * WG_STAGE_BYTES + op_off);
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
           const int r = r0 + rr;
           const uint32_t off = uint32_t(r * 128 + (((((c >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4));
-          uint8_t* hi_p = base + off;
-          const float4 v = *reinterpret_cast<const float4*>(hi_p);
+          const float4 v = lds128(base + off);
           float4 h, l;
           h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
           l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-          *reinterpret_cast<float4*>(hi_p) = h;
-          *reinterpret_cast<float4*>(lo_base + off) = l;
+          sts128(base + off, h);
+          sts128(lo_base + off, l);
           colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w;
         }
       }

@@ -184,6 +184,7 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       for (int64_t nt = t_beg; nt < t_end; ++nt) {
         const int64_t n0 = nt * SC_BN;
         int32_t* ts = types_s + parity * SC_BN;
+        const uint32_t ts_addr = smem_u32(ts);
         parity ^= 1;
         ts[trow] = t_next;
         t_next = type_of(nt + 1);      // in flight while this tile is processed
@@ -196,7 +197,7 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
           uint32_t mask = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int t = ts[c0 + j];
+            const int t = lds32i(ts_addr + (c0 + j) * 4);
             const bool e = t != -2 && (rt < 0 || t == rt) && (kept < KP || __uint_as_float(r[j]) > thr);
             mask |= uint32_t(e) << j;
           }
