@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the P-Companion hot path on B200 (contract: see the task statement / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload gat|retrieval]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload gat|retrieval|pcompanion]
 
 Default workload = BASELINE.json configs[1]: synthetic BPG with 1 M products / ~20 M co-view
 edges per GPU, one step = full-graph Product2Vec GAT forward + triplet hinge + backward + Adam
@@ -105,6 +105,8 @@ def run_ours(args):
 
     if args.workload == "retrieval":
         return run_retrieval(args, rank, world, dev)
+    if args.workload == "pcompanion":
+        return run_pcompanion(args, rank, world, dev)
     if world > 1:
         from pcompanion_b200.distributed import run_partitioned_bench
         return run_partitioned_bench(args, rank, world, dev)
@@ -220,6 +222,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
 
+    csr_build = time_csr_build(graph, peak)
     cpu = None if args.skip_cpu else cpu_baseline_gat(bpg, graph, cfg, seconds=15.0)
     line = {
         "metric": "gat_edges_per_sec_fwd_bwd", "value": e / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": 1,
@@ -229,13 +232,101 @@ def run_ours(args):
                                "(FFN+QKV+out-proj per node, triplet hinge on 131072 triplets, Adam), 1xB200",
                    "nodes": n, "edges": e, "heads": 4, "dropout": cfg.DROPOUT, "triplets": TRIPLETS,
                    "l2": "working set (K|V 1 GB, Q 0.5 GB) exceeds the 126 MB L2; no flush needed",
-                   "csr_build_s": round(build_s, 3)},
+                   "bpg_build_s": round(build_s, 3)},
+        "csr_build": csr_build,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "e2e": {"value": e / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": x_host.numel() * 4 + trip_host.numel() * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "loss": float(loss.item()),
     }
     print(json.dumps(line))
+
+
+def run_pcompanion(args, rank, world, dev):
+    """C3: P-Companion joint training step (type transition + item prediction, 0.8 item + 0.2 type hinge, Adam) on a
+    frozen 1 M-product table, NUM_TYPES = 34,800 (reference default); data parallel over samples (replicated model,
+    gradient all-reduce)."""
+    import torch.distributed as dist
+    import pcompanion_b200 as pc
+    from pcompanion_b200 import _lib
+    from pcompanion_b200.distributed import allreduce_gradients
+    p, b = 1_000_000, args.batch
+    cfg = make_cfg(dev)
+    t = cfg.NUM_TYPES
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    table = torch.randn(p, 128, generator=g, device=dev)
+    torch.manual_seed(SEED)
+    model = pc.PCompanion(cfg, table).to(dev).train()
+    opt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=cfg.LEARNING_RATE)
+    host = {"query_ids": torch.randint(0, p, (b,)), "query_types": torch.randint(0, t, (b,)),
+            "positive_types": torch.randint(0, t, (b, 1)), "negative_types": torch.randint(0, t, (b, 1)),
+            "positive_items": torch.randn(b, 128), "negative_items": torch.randn(b, 128)}
+    host = {k: v.pin_memory() for k, v in host.items()}
+    batch = {k: v.to(dev) for k, v in host.items()}
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(bt):
+        out = model(bt)
+        loss = model.compute_loss(bt, out)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(model)
+        opt.step()
+        return loss
+
+    def step_e2e():
+        loss_host.copy_(step({k: v.to(dev, non_blocking=True) for k, v in host.items()}).detach(), non_blocking=True)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step(batch)
+    sampler = ClockSampler(dev.index)
+    l0 = _lib.LAUNCHES
+    ms = timed(lambda: step(batch), args.steps)
+    launches = _lib.LAUNCHES - l0
+    clocks = sampler.stop()
+    step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        # bytes that must move per sample: the [T] similarity row is written once in forward and its (dense) gradient
+        # written + read once in backward; the [T,64] type table and its Adam state are per step, not per sample
+        algo = b * t * 4 * 3 + 5 * t * 64 * 4 * 2
+        line = {"metric": "pcompanion_samples_per_sec_fwd_loss_bwd", "value": b * world / (ms * 1e-3), "unit": "samples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C3: P-Companion joint step, 1M-product frozen table, {t} types, batch {b} per GPU, "
+                                       "K_t=3, alpha 0.8, Adam", "batch": b, "types": t,
+                           "l2": "similarity matrix [B,T] fp32 = %.1f GB per step" % (b * t * 4 / 1e9)},
+                "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "note": "whole step against the [B,T] similarity write + gradient write/read and the type-table "
+                                     "optimiser traffic; the [B,64]x[64,T] products are library fp32 GEMMs (cuBLAS), our kernels "
+                                     "do the type top-3 and both hinge losses"},
+                "cpu_baseline": None, "clocks": clocks,
+                "e2e": {"value": b * world / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * world,
+                        "d2h_bytes_per_step": 4 * world},
+                "gpu_launches": launches}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_retrieval(args, rank, world, dev):
@@ -312,6 +403,35 @@ def run_retrieval(args, rank, world, dev):
 
 
 # ----------------------------------------------------------------------------- CPU baseline / reference arm
+def time_csr_build(graph, peak, reps: int = 3):
+    """Part (1) of the path on its own: shuffled (src, dst) edge list -> pack, radix sort, unique, CSR, then the
+    transposed lists (CSC) - device time from CUDA events.  SURVEY 8(d): ~100 algorithmic bytes per edge for the CSR
+    (4 radix passes x 8 B read + write, + unique + scan); the CSC build costs about the same again."""
+    from pcompanion_b200 import ops
+    e = graph.num_edges
+    rows = torch.repeat_interleave(torch.arange(graph.n_rows, device=graph.col.device, dtype=torch.int32),
+                                   (graph.rowptr[1:] - graph.rowptr[:-1]))
+    perm = torch.randperm(e, device=rows.device)
+    src, dst = rows[perm].contiguous(), graph.col[perm].contiguous()
+    del rows, perm
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    csr_ms, csc_ms = [], []
+    for _ in range(reps + 1):
+        ev[0].record()
+        g2, _ = ops.build_csr(src, dst, graph.n_rows, graph.n_cols)
+        ev[1].record()
+        g2.transposed()
+        ev[2].record()
+        torch.cuda.synchronize()
+        csr_ms.append(ev[0].elapsed_time(ev[1])); csc_ms.append(ev[1].elapsed_time(ev[2]))
+    ok = bool(torch.equal(g2.col, graph.col) and torch.equal(g2.rowptr, graph.rowptr))
+    a, b = min(csr_ms[1:]), min(csc_ms[1:])
+    return {"edges": e, "csr_ms": round(a, 3), "csc_ms": round(b, 3), "edges_per_s": e / ((a + b) * 1e-3),
+            "csr_edges_per_s": e / (a * 1e-3), "csr_algo_gbs": round(100 * e / (a * 1e-3) / 1e9, 1),
+            "csr_frac_of_hbm": round(100 * e / (a * 1e-3) / 1e9 / peak, 4), "rebuilt_equals_original": ok,
+            "note": "includes one host sync for the data-dependent unique count"}
+
+
 def padded_batches(graph_rowptr, graph_col, feats, n_batches, batch, gen):
     """Index-based collate (no Python sets): dense zero-padded neighbour tensors exactly as
     data_loader.py:171-206 would build them for `batch` destinations."""
@@ -452,7 +572,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gat", choices=["gat", "retrieval"])
+    ap.add_argument("--workload", default="gat", choices=["gat", "retrieval", "pcompanion"])
+    ap.add_argument("--batch", type=int, default=4096, help="pcompanion: samples per GPU per step")
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--skip-cpu", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
     ap.add_argument("--dense", action="store_true", help="retrieval: dense tcgen05 scoring + mask + top-K instead of the segmented kernel")

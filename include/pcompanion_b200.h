@@ -219,6 +219,23 @@ int pc_topk_merge(const double* scores, const int64_t* idx, int64_t rows, int li
 int pc_rows_gather(const float* table, const int64_t* index, int64_t n, int width, float* out, pc_stream_t stream);
 int pc_rows_scatter_add(const float* rows, const int64_t* index, int64_t n, int width, float* table,
                         pc_stream_t stream);
+/* Owner-side reduction of the returned halo partials in one pass: table[r, :] += sum over p = 0..world-1, in that
+ * order, of rows[slot[p * n + r], :] for slot >= 0 (slot int32 [world, n], -1 = peer p holds no partial of row r). */
+int pc_rows_reduce_peers(const float* rows, const int32_t* slot, int world, int64_t n, int width, float* table,
+                         pc_stream_t stream);
+/* Fused halo pack + exchange over NVLink / NVSwitch peer memory, ONE launch for all peers (new: the reference has
+ * no multi-GPU path).  Rows j in [row_off[p], row_off[p+1]) of the send list go to peer p:
+ *   src = table + (index ? index[j] : src_row0[p] + (j - row_off[p])) * ld
+ *   dst = peer_base[p] + (dst_row0[p] + (j - row_off[p])) * width
+ * peer_base[p] is the peer's halo table as mapped into THIS process (CUDA IPC / symmetric memory).  row_off
+ * [world+1], peer_base, src_row0, dst_row0 [world] are HOST arrays (world <= PC_MAX_PEERS).  The send list is
+ * walked cyclically from row `first_row` (rank r passes row_off[(r+1) % world], so that the ranks do not all store
+ * into the same GPU at the same time).  Visibility on the peers is the caller's job: a stream-ordered cross-rank
+ * barrier after the launch. */
+#define PC_MAX_PEERS 16
+int pc_halo_push(const float* table, int64_t ld, const int64_t* index, int world, const int64_t* row_off,
+                 float* const* peer_base, const int64_t* src_row0, const int64_t* dst_row0, int64_t first_row,
+                 int width, pc_stream_t stream);
 /* out[r, :] = sum_{e in [rowptr[r], rowptr[r+1])} rows[col[e], :] in ascending e, zeros for empty rows: the
  * deterministic gradient of a row gather table[index] (the index list is turned into a CSR with the BPG sort
  * kernels), used for the embedding rows a triplet batch touches (product2vec.py:132-134 on a shared table). */

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "pc_topk_merge": (c_int, [P, P, c_int64, c_int, c_int, P, P, P]),
     "pc_rows_gather": (c_int, [P, P, c_int64, c_int, P, P]),
     "pc_rows_scatter_add": (c_int, [P, P, c_int64, c_int, P, P]),
+    "pc_rows_reduce_peers": (c_int, [P, P, c_int, c_int64, c_int, P, P]),
+    "pc_halo_push": (c_int, [P, c_int64, P, c_int, P, P, P, P, c_int64, c_int, P]),
     "pc_rows_segment_sum": (c_int, [P, P, P, c_int64, c_int, P, P]),
 }
 

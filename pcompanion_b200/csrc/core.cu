@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pc {
@@ -75,10 +77,104 @@ rows_segment_sum_kernel(const float4* __restrict__ rows, const int64_t* __restri
   }
 }
 
+// table[r, :] += sum over peers p = 0..world-1 (in that order) of rows[slot[p * n + r], :] where slot >= 0: the
+// owner-side reduction of returned halo partials as ONE pass over the local rows (fixed order => deterministic).
+__global__ void __launch_bounds__(256)
+rows_reduce_peers_kernel(const float4* __restrict__ rows, const int32_t* __restrict__ slot, int world, int64_t n, int width4,
+                         float4* __restrict__ table) {
+  const int64_t r = int64_t(blockIdx.x) * 8 + warp_id();
+  if (r >= n) return;
+  int32_t mine = lane_id() < world ? slot[int64_t(lane_id()) * n + r] : -1;
+  if (__ballot_sync(0xffffffffu, mine >= 0) == 0) return;
+  float4* dst = table + r * width4;
+  for (int c = lane_id(); c < width4; c += 32) {
+    float4 a = dst[c];
+    for (int p = 0; p < world; ++p) {
+      const int32_t s = __shfl_sync(0xffffffffu, mine, p);
+      if (s < 0) continue;
+      const float4 b = ld_stream4(rows + int64_t(s) * width4 + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dst[c] = a;
+  }
+}
+
+// Fused halo pack + exchange: every row of the send list is read from the local table (through `index`, or a
+// contiguous run when index == nullptr) and stored straight into the owner / consumer GPU's table over NVLink.
+struct HaloPushArgs {
+  int64_t row_off[PC_MAX_PEERS + 1];
+  float4* base[PC_MAX_PEERS];
+  int64_t src_row0[PC_MAX_PEERS];
+  int64_t dst_row0[PC_MAX_PEERS];
+  int64_t first_row;
+  int world;
+};
+
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const float4* __restrict__ table, int64_t ld4, const int64_t* __restrict__ index, int width4,
+                 const __grid_constant__ HaloPushArgs a) {
+  const int64_t total = a.row_off[a.world];
+  for (int64_t v = int64_t(blockIdx.x) * 8 + warp_id(); v < total; v += int64_t(gridDim.x) * 8) {
+    int64_t j = v + a.first_row;          // cyclic walk: every rank starts with a different peer's rows
+    if (j >= total) j -= total;
+    int p = 0;
+    while (j >= a.row_off[p + 1]) ++p;
+    const int64_t k = j - a.row_off[p];
+    const float4* src = table + (index ? index[j] : a.src_row0[p] + k) * ld4;
+    float4* dst = a.base[p] + (a.dst_row0[p] + k) * width4;
+    for (int c = lane_id(); c < width4; c += 32) dst[c] = ldg4(src + c);
+  }
+}
+
 }  // namespace
 }  // namespace pc
 
 using namespace pc;
+
+extern "C" int pc_rows_reduce_peers(const float* rows, const int32_t* slot, int world, int64_t n, int width, float* table,
+                                    pc_stream_t stream) {
+  PC_REQUIRE(world >= 1 && world <= PC_MAX_PEERS, PC_ERR_UNSUPPORTED, "rows_reduce_peers: world=%d outside [1,%d]", world,
+             PC_MAX_PEERS);
+  PC_REQUIRE(n >= 0 && width > 0 && width % 4 == 0, PC_ERR_INVALID, "rows_reduce_peers: bad n=%lld width=%d", (long long)n, width);
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(rows && slot && table, PC_ERR_INVALID, "rows_reduce_peers: null pointer");
+  rows_reduce_peers_kernel<<<unsigned(ceil_div(n, 8)), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(rows), slot, world, n, width / 4, reinterpret_cast<float4*>(table));
+  PC_LAUNCH_CHECK();
+  return PC_OK;
+}
+
+extern "C" int pc_halo_push(const float* table, int64_t ld, const int64_t* index, int world, const int64_t* row_off,
+                            float* const* peer_base, const int64_t* src_row0, const int64_t* dst_row0, int64_t first_row,
+                            int width, pc_stream_t stream) {
+  PC_REQUIRE(world >= 1 && world <= PC_MAX_PEERS, PC_ERR_UNSUPPORTED, "halo_push: world=%d outside [1,%d]", world, PC_MAX_PEERS);
+  PC_REQUIRE(width > 0 && width % 4 == 0 && ld % 4 == 0 && ld >= width, PC_ERR_INVALID, "halo_push: bad width=%d ld=%lld", width,
+             (long long)ld);
+  PC_REQUIRE(row_off && peer_base && dst_row0 && (index || src_row0), PC_ERR_INVALID, "halo_push: null pointer");
+  HaloPushArgs a;
+  a.world = world;
+  a.row_off[0] = row_off[0];
+  PC_REQUIRE(row_off[0] == 0, PC_ERR_INVALID, "halo_push: row_off[0] must be 0");
+  for (int p = 0; p < world; ++p) {
+    PC_REQUIRE(row_off[p + 1] >= row_off[p], PC_ERR_INVALID, "halo_push: row_off not ascending at peer %d", p);
+    PC_REQUIRE(row_off[p + 1] == row_off[p] || peer_base[p], PC_ERR_INVALID, "halo_push: rows for peer %d but no base pointer", p);
+    a.row_off[p + 1] = row_off[p + 1];
+    a.base[p] = reinterpret_cast<float4*>(peer_base[p]);
+    a.src_row0[p] = src_row0 ? src_row0[p] : 0;
+    a.dst_row0[p] = dst_row0[p];
+  }
+  const int64_t total = row_off[world];
+  if (total == 0) return PC_OK;
+  PC_REQUIRE(table, PC_ERR_INVALID, "halo_push: null table");
+  PC_REQUIRE(first_row >= 0 && first_row <= total, PC_ERR_INVALID, "halo_push: first_row=%lld outside [0,%lld]",
+             (long long)first_row, (long long)total);
+  a.first_row = first_row == total ? 0 : first_row;
+  const int64_t blocks = std::min<int64_t>(ceil_div(total, 8), int64_t(sm_count()) * 32);
+  halo_push_kernel<<<unsigned(blocks), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(table), ld / 4, index,
+                                                                    width / 4, a);
+  PC_LAUNCH_CHECK();
+  return PC_OK;
+}
 
 extern "C" int pc_abi_version(void) { return PC_ABI_VERSION; }
 

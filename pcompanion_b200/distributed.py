@@ -29,9 +29,13 @@ from . import ops
 
 
 class HaloPlan:
-    """Which rows every rank sends / receives, and the CSR remapped to [local | halo] column space."""
+    """Which rows every rank sends / receives, and the CSR remapped to [local | halo] column space.
 
-    def __init__(self, rowptr: torch.Tensor, col_global: torch.Tensor, bounds: List[int], rank: int, group=None):
+    ``rowptr=None`` gives a plain row-fetch plan: ``col_global`` is any list of global node ids (the
+    positives / negatives of a triplet batch) and ``col_ext`` their positions in the
+    [local | halo] table that ``halo_gather`` returns."""
+
+    def __init__(self, rowptr: Optional[torch.Tensor], col_global: torch.Tensor, bounds: List[int], rank: int, group=None):
         self.group = group
         self.rank = rank
         self.world = len(bounds) - 1
@@ -54,13 +58,39 @@ class HaloPlan:
         want = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=dev)
         self._a2a(want, remote.contiguous(), self.send_counts, self.recv_counts)
         self.send_idx = (want - base).contiguous()                    # local row ids, grouped by destination peer
+        # slot[p, r] = position of local row r in peer p's chunk of the returned rows (-1: p does not use row r);
+        # ids are unique inside one chunk, so the owner-side reduction is one deterministic pass over the local rows
+        self.slot = torch.full((self.world, self.n_local), -1, dtype=torch.int32, device=dev)
+        off = 0
+        for p, cnt in enumerate(self.send_counts):
+            if cnt:
+                self.slot[p, self.send_idx[off: off + cnt]] = torch.arange(off, off + cnt, dtype=torch.int32, device=dev)
+            off += cnt
         # remap columns: local -> [0, n_local), remote -> n_local + position in `remote`
         is_local = (col >= base) & (col < end)
         ext = torch.where(is_local, col - base, self.n_local + torch.searchsorted(remote, col))
         self.graph = ops.CSRGraph(rowptr.contiguous(), ext.to(torch.int32).contiguous(), self.n_local,
-                                  self.n_local + self.n_halo) if col.is_cuda else None
+                                  self.n_local + self.n_halo) if (col.is_cuda and rowptr is not None) else None
         self.col_ext = ext
         self.rowptr = rowptr
+        self.peer: Optional["PeerHalo"] = None
+
+    def enable_peer_memory(self, width: int = 256) -> bool:
+        """Move the halo rows with pc_halo_push over NVLink peer memory (``PeerHalo``) instead of the NCCL all-to-all.
+        Collective: every rank must call it.  Returns False (and keeps the NCCL transport) when symmetric memory cannot
+        be set up on this system; PC_HALO_TRANSPORT=nccl forces that."""
+        if self.world == 1 or not self.send_idx.is_cuda or os.environ.get("PC_HALO_TRANSPORT", "") == "nccl":
+            return False
+        ok = torch.ones(1, device=self.send_idx.device)
+        try:
+            peer = PeerHalo(self, width)
+        except Exception as e:   # noqa: BLE001 - any failure (driver, container permissions) means: stay on NCCL
+            self.peer_error = f"{type(e).__name__}: {e}"
+            peer = None
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        self.peer = peer if ok.item() > 0 else None
+        return self.peer is not None
 
     @staticmethod
     def _unique_sorted(col: torch.Tensor) -> torch.Tensor:
@@ -93,6 +123,91 @@ class HaloPlan:
         return self.n_halo * width * 4
 
 
+class PeerHalo:
+    """Halo rows moved by our own kernel over NVLink / NVSwitch peer memory instead of a NCCL all-to-all.
+
+    Every rank keeps its [local | halo] K|V table and its buffer of returned dK|dV partials in symmetric
+    memory (torch.distributed._symmetric_memory: same-size allocations whose peer mappings are exchanged once).
+    Forward: ONE launch of pc_halo_push gathers the rows the peers asked for and stores them straight into the
+    peers' tables (no pack buffer, no receive copy).  Backward: each contiguous run of halo partials is copied into
+    its owner's return buffer by the copy engines (SMs stay free for the overlapped compute); the owner adds the
+    runs in fixed peer order in one pass (pc_rows_reduce_peers).  Cross-rank ordering is a
+    stream-ordered 1-element NCCL all-reduce before the first store (the peers are done reading the previous
+    contents) and after the last one (the stores have landed)."""
+
+    def __init__(self, plan: "HaloPlan", width: int = 256):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        self.plan, self.width = plan, width
+        world, rank, group = plan.world, plan.rank, plan.group if plan.group is not None else dist.group.WORLD
+        dev = plan.send_idx.device
+        mine = torch.tensor(plan.recv_counts, dtype=torch.int64, device=dev)
+        allc = torch.empty(world, world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=group)
+        c = allc.tolist()                                             # c[q][p] = rows rank q receives from rank p
+        n_loc = [plan.bounds[q + 1] - plan.bounds[q] for q in range(world)]
+        self.table_rows = max(n_loc[q] + sum(c[q]) for q in range(world))
+        self.return_rows = max(1, max(sum(c[q][p] for q in range(world)) for p in range(world)))
+        self._kv = symm.empty(self.table_rows * width, dtype=torch.float32, device=dev)
+        self._ret = symm.empty(self.return_rows * width, dtype=torch.float32, device=dev)
+        h_kv = symm.rendezvous(self._kv, group.group_name)
+        h_ret = symm.rendezvous(self._ret, group.group_name)
+        self._handles = (h_kv, h_ret)
+        i64, fp = ctypes.c_int64 * (world + 1), ctypes.c_void_p * world
+        i64w = ctypes.c_int64 * world
+        # forward: my send list is grouped by destination peer p; in p's table my rows follow p's own rows and the
+        # rows of the ranks before me
+        off = [0]
+        for p in range(world):
+            off.append(off[-1] + plan.send_counts[p])
+        self._f_off = i64(*off)
+        self._f_first = off[(rank + 1) % world]                       # staggered start: rank r begins with peer r+1
+        self._f_base = fp(*[int(h_kv.buffer_ptrs[p]) if plan.send_counts[p] else None for p in range(world)])
+        self._f_dst = i64w(*[n_loc[p] + sum(c[p][:rank]) for p in range(world)])
+        # reverse: my halo partials are grouped by owner p; in p's return buffer (grouped by the rank that holds the
+        # partials) my run follows the runs of the ranks before me
+        roff = [0]
+        for p in range(world):
+            roff.append(roff[-1] + c[rank][p])
+        self._r_copy = []
+        for p in range(world):
+            cnt, dst0 = c[rank][p], sum(c[q][p] for q in range(rank))
+            view = h_ret.get_buffer(p, (self.return_rows, width), torch.float32)[dst0: dst0 + cnt] if cnt else None
+            self._r_copy.append((n_loc[rank] + roff[p], cnt, view))
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._group = group
+        self.version = 0
+        self.side = torch.cuda.Stream(device=dev)
+
+    def table(self, rows: int) -> torch.Tensor:
+        """[rows, width] view of the symmetric K|V table; a new forward invalidates the previous contents."""
+        self.version += 1
+        return self._kv[: rows * self.width].view(rows, self.width)
+
+    def returned(self) -> torch.Tensor:
+        n = self.plan.send_idx.numel()
+        return self._ret[: n * self.width].view(n, self.width)
+
+    def barrier(self) -> None:
+        dist.all_reduce(self._flag, group=self._group)
+
+    def push_forward(self, table_local: torch.Tensor) -> None:
+        from ._lib import call, dev, stream
+        call("pc_halo_push", dev(table_local, torch.float32, "table"), table_local.stride(0),
+             dev(self.plan.send_idx, torch.int64, "send_idx"), self.plan.world, self._f_off, self._f_base, None, self._f_dst,
+             self._f_first, self.width, stream())
+
+    def push_reverse(self, dkv_ext: torch.Tensor) -> None:
+        """Every owner's run of halo partials is contiguous on both sides, so it travels as a plain peer copy on the
+        copy engines: the SMs stay with the dst-major pass and the GEMMs this overlaps with.  (pc_halo_push with
+        index = NULL does the same from the SMs: measured 9 -> 4.6 ms of wgrad slowdown at 4 GPUs, so not used here.)"""
+        world, rank = self.plan.world, self.plan.rank
+        for k in range(1, world + 1):                                 # staggered: rank r starts with owner r+1
+            src0, cnt, view = self._r_copy[(rank + k) % world]
+            if cnt:
+                view.copy_(dkv_ext[src0: src0 + cnt])
+
+
 class _HaloGather(torch.autograd.Function):
     """[n_local, W] -> [n_local + n_halo, W]; backward returns the halo gradients to their owners."""
 
@@ -115,16 +230,47 @@ class _HaloGather(torch.autograd.Function):
         d_local = d_ext[: plan.n_local].clone()
         returned = torch.empty(plan.send_idx.numel(), w, dtype=d_ext.dtype, device=d_ext.device)
         plan.reverse_exchange(d_ext[plan.n_local:].contiguous(), returned)
-        off = 0
-        for cnt in plan.send_counts:            # fixed peer order; ids are unique inside one peer's chunk
-            if cnt:
-                ops.rows_scatter_add_(d_local, plan.send_idx[off: off + cnt], returned[off: off + cnt])
-            off += cnt
+        ops.rows_reduce_peers_(d_local, returned, plan.slot)          # fixed peer order: deterministic
         return d_local, None
 
 
 def halo_gather(table: torch.Tensor, plan: HaloPlan) -> torch.Tensor:
     return _HaloGather.apply(table, plan)
+
+
+def partition_edges(rows: torch.Tensor, cols: torch.Tensor, bounds: List[int], rank: int, group=None):
+    """Distributed CSR build.  Every rank holds an arbitrary slice of the global edge list
+    (aggregating node ``rows``, neighbour ``cols``, global ids, duplicates allowed - bpg.py:19-22 semantics).
+    Keys row<<32|col are sorted locally, cut at the owners' row bounds, exchanged with ONE all-to-all, then
+    sorted / deduplicated by the owner.  Returns (rowptr int64 [n_local + 1], col_global int32 [E_local]) with
+    ascending neighbours per row - the input of ``HaloPlan``."""
+    world = len(bounds) - 1
+    base, n_local = bounds[rank], bounds[rank + 1] - bounds[rank]
+    dev = rows.device
+    cuda = rows.is_cuda
+    mask = ops.digit_mask_for(bounds[-1])
+    if cuda:
+        keys = ops.sort_keys_(ops.pack_keys(rows.to(torch.int32), cols.to(torch.int32)), mask)
+    else:   # gloo tests of the exchange logic on CPU tensors
+        keys = torch.sort((rows.to(torch.int64) << 32) | cols.to(torch.int64)).values
+    cuts = torch.searchsorted(keys, torch.tensor(bounds, dtype=torch.int64, device=dev) << 32)
+    send_counts = (cuts[1:] - cuts[:-1]).tolist()
+    if world > 1:
+        counts_in = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(counts_in, torch.tensor(send_counts, dtype=torch.int64, device=dev), group=group)
+        recv_counts = counts_in.tolist()
+        mine = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(mine, keys[int(cuts[0]): int(cuts[-1])].contiguous(), output_split_sizes=recv_counts,
+                               input_split_sizes=send_counts, group=group)
+    else:
+        mine = keys[int(cuts[0]): int(cuts[-1])].clone()
+    mine -= base << 32                                        # rows become local ids; order is unchanged
+    if cuda:
+        mine = ops.unique_sorted(ops.sort_keys_(mine, mask))
+        return ops.csr_from_sorted_keys(mine, n_local)
+    mine = torch.unique(mine)
+    rowptr = torch.searchsorted(mine, torch.arange(n_local + 1, dtype=torch.int64) << 32)
+    return rowptr, (mine & 0xFFFFFFFF).to(torch.int32)
 
 
 def forward_graph_partitioned(model, x_local: torch.Tensor, plan: HaloPlan, sync_bn: bool = True) -> torch.Tensor:
@@ -159,24 +305,36 @@ def run_partitioned_bench(args, rank: int, world: int, dev: torch.device) -> Non
     n_total = n_loc * world
     bounds = [i * n_loc for i in range(world + 1)]
     g = torch.Generator(device=dev).manual_seed(B.SEED + 100 + rank)
-    rows = torch.randint(0, n_loc, (e_loc,), generator=g, device=dev, dtype=torch.int32)
+    # every rank draws its share of the GLOBAL edge list; the owners of the rows get them through the distributed
+    # CSR build (one all-to-all of keys, then local sort / unique) - timed separately, outside the step
+    rows = torch.randint(0, n_total, (e_loc,), generator=g, device=dev, dtype=torch.int32)
     cols = torch.randint(0, n_total, (e_loc,), generator=g, device=dev, dtype=torch.int32)
-    csr, _ = ops.build_csr(rows, cols, n_loc, n_total)
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    rowptr, col_global = partition_edges(rows, cols, bounds, rank)
+    torch.cuda.synchronize(); dist.barrier(); build_s = time.perf_counter() - t0
     del rows, cols
-    plan = HaloPlan(csr.rowptr, csr.col, bounds, rank)
+    plan = HaloPlan(rowptr, col_global, bounds, rank)
     plan.graph.transposed()
-    e_local = csr.num_edges
+    transport = ("pc_halo_push: gather + NVLink stores into the peers' symmetric-memory tables, one launch per direction"
+                 if plan.enable_peer_memory() else
+                 "NCCL all_to_all_single (" + getattr(plan, "peer_error", "peer memory disabled") + ")")
+    e_local = col_global.numel()
     x = torch.randn(n_loc, 128, generator=g, device=dev)
     cfg = B.make_cfg(dev)
     torch.manual_seed(B.SEED)                      # identical replicated weights on every rank
     model = pc.Product2Vec(cfg).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
-    trip = torch.randint(0, n_loc, (B.TRIPLETS, 2 + B.KNEG), generator=g, device=dev)
+    # triplets: anchors are local, positives / negatives are any product of the global graph; their rows come from
+    # the owners through a row-fetch plan (built once: the index batch is fixed, as in the 1-GPU leg)
+    trip_global = torch.cat([torch.randint(0, n_loc, (B.TRIPLETS, 1), generator=g, device=dev) + bounds[rank],
+                             torch.randint(0, n_total, (B.TRIPLETS, 1 + B.KNEG), generator=g, device=dev)], dim=1)
+    fetch = HaloPlan(None, trip_global.reshape(-1), bounds, rank)
+    trip = fetch.col_ext.view_as(trip_global).contiguous()
     x_host, trip_host = x.cpu().pin_memory(), trip.cpu().pin_memory()
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def step(xd, tr):
-        emb = forward_graph_partitioned(model, xd, plan)
+        emb = halo_gather(forward_graph_partitioned(model, xd, plan), fetch)
         loss = model.triplet_loss_indexed(emb, tr[:, 0], tr[:, 1], tr[:, 2:])
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -184,10 +342,29 @@ def run_partitioned_bench(args, rank: int, world: int, dev: torch.device) -> Non
         opt.step()
         return loss
 
+    # end-to-end leg: the next step's inputs are copied from pinned host memory on a side stream while this step
+    # computes (double-buffered staging, as in the 1-GPU leg)
+    copy_stream = torch.cuda.Stream()
+    stage = [(torch.empty_like(x), torch.empty_like(trip), torch.cuda.Event()) for _ in range(2)]
+    e2e_state = {"i": 0}
+
+    def prefetch(slot):
+        xs, ts, ev = stage[slot]
+        with torch.cuda.stream(copy_stream):
+            xs.copy_(x_host, non_blocking=True)
+            ts.copy_(trip_host, non_blocking=True)
+            ev.record(copy_stream)
+
     def step_e2e():
-        xd = torch.empty_like(x); xd.copy_(x_host, non_blocking=True)
-        tr = torch.empty_like(trip); tr.copy_(trip_host, non_blocking=True)
-        loss_host.copy_(step(xd, tr).detach(), non_blocking=True)
+        i = e2e_state["i"]
+        if i == 0:
+            prefetch(0)
+        xs, ts, ev = stage[i % 2]
+        torch.cuda.current_stream().wait_event(ev)
+        copy_stream.wait_stream(torch.cuda.current_stream())       # the other slot was last read by the previous step
+        prefetch((i + 1) % 2)
+        e2e_state["i"] = i + 1
+        loss_host.copy_(step(xs, ts).detach(), non_blocking=True)
 
     def timed(fn, steps):
         torch.cuda.synchronize(); dist.barrier()
@@ -208,12 +385,23 @@ def run_partitioned_bench(args, rank: int, world: int, dev: torch.device) -> Non
     ms, loss = timed(lambda: step(x, trip), args.steps)
     launches = _lib.LAUNCHES - launches0
     clocks = sampler.stop()
+    # where the step goes: CUDA events around every C-ABI call of two more steps (the difference to ms_per_step is
+    # exchange time that compute did not hide, plus the optimiser and index plumbing)
+    _lib.PROFILE = []
+    for _ in range(2):
+        step(x, trip)
+    torch.cuda.synchronize()
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    per = {}
+    for name, s0, s1 in prof:
+        per[name] = per.get(name, 0.0) + s0.elapsed_time(s1) / 2
+    abi_ms = {k: round(v, 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
     for _ in range(2):
         step_e2e()
     e2e_ms, _ = timed(step_e2e, args.steps)
-    tot = torch.tensor([e_local, plan.n_halo], dtype=torch.float64, device=dev)
+    tot = torch.tensor([e_local, plan.n_halo, fetch.n_halo], dtype=torch.float64, device=dev)
     dist.all_reduce(tot)
-    e_total, halo_total = tot.tolist()
+    e_total, halo_total, fetch_total = tot.tolist()
     if rank == 0:
         peak, peak_src = B.measured_peaks()
         algo = (3152 * e_local + 3676 * n_loc)
@@ -223,14 +411,19 @@ def run_partitioned_bench(args, rank: int, world: int, dev: torch.device) -> Non
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C5-style: node-partitioned synthetic BPG, {n_loc} products / ~{e_loc} co-view edges per GPU x {world} GPUs, "
                                    "columns uniform over the global range, Product2Vec GAT fwd+bwd with NCCL all-to-all halo exchange of "
-                                   "K|V rows (fwd) and dK|dV partials (bwd), gradient all-reduce, Adam",
+                                   "K|V rows (fwd) and dK|dV partials (bwd), triplet positives / negatives fetched from their owners, "
+                                   "gradient all-reduce, Adam",
                        "nodes_total": n_total, "edges_total": int(e_total), "halo_rows_per_gpu": int(halo_total / world),
-                       "halo_bytes_per_gpu_per_direction": int(halo_total / world) * 1024, "batchnorm": "synchronised (all-reduce of the [2,256] column sums)",
+                       "halo_bytes_per_gpu_per_direction": int(halo_total / world) * 1024,
+                       "triplet_rows_fetched_per_gpu": int(fetch_total / world), "halo_transport": transport,
+                       "csr_build": {"what": "distributed: all-to-all of edge keys by row owner + local radix sort / unique / CSR",
+                                     "seconds": build_s, "edges_per_s": e_total / build_s}, "batchnorm": "synchronised (all-reduce of the [2,256] column sums)",
                        "l2": "working set exceeds the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "note": "whole step per GPU against the sparse-kernel algorithmic bytes (3152 B/edge + 3676 B/node); "
                                  "the halo all-to-all moves halo_bytes over NVLink each way on top"},
+            "abi_ms_per_step": abi_ms, "abi_total_ms_per_step": round(sum(abi_ms.values()), 3),
             "clocks": clocks,
             "e2e": {"value": e_total / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": (x_host.numel() * 4 + trip_host.numel() * 8) * world, "d2h_bytes_per_step": 4 * world},

@@ -27,8 +27,14 @@ from . import ops
 F32 = torch.float32
 
 
-def _allreduce_sums(sums: torch.Tensor, count: int, group, sync: bool):
+def _allreduce_sums(sums: torch.Tensor, count: int, group, sync: bool, total: Optional[int] = None):
+    """Global column sums (+ global row count) for SyncBN.  When the caller knows the global row count (`total`,
+    from the partition bounds) nothing is read back to the host."""
     if sync and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if total is not None:
+            sums = sums.clone()
+            dist.all_reduce(sums, group=group)
+            return sums, total
         buf = torch.cat([sums.reshape(-1), torch.tensor([float(count)], dtype=sums.dtype, device=sums.device)])
         dist.all_reduce(buf, group=group)
         return buf[:-1].reshape(sums.shape), int(round(buf[-1].item()))
@@ -47,7 +53,8 @@ class _P2VGraphLayer(torch.autograd.Function):
         n = x.shape[0]
         z1 = ops.linear_tc(x, w0, b0)
         if training:
-            sums, count = _allreduce_sums(ops.col_stats(z1), n, group, sync_bn)
+            total = plan.bounds[-1] - plan.bounds[0] if plan is not None else None
+            sums, count = _allreduce_sums(ops.col_stats(z1), n, group, sync_bn, total)
             mean64 = sums[0] / count
             var64 = (sums[1] / count - mean64 * mean64).clamp_(min=0.0)
             if run_mean is not None:
@@ -67,9 +74,18 @@ class _P2VGraphLayer(torch.autograd.Function):
         h = ops.linear_tc(a2, w5, b5)
         qg = torch.empty(n, 256, dtype=F32, device=x.device)
         n_ext = graph.n_cols
-        kv = torch.empty(n_ext, 256, dtype=F32, device=x.device)
+        peer = plan.peer if plan is not None else None
+        kv = peer.table(n_ext) if peer is not None else torch.empty(n_ext, 256, dtype=F32, device=x.device)
         if plan is None:
             ops.linear_tc(h, w_in, b_in, split=128, out0=qg[:, :128], out1=kv[:n])
+        elif peer is not None:
+            # K|V straight into the symmetric table; one kernel gathers the rows the peers need and stores them into
+            # the peers' tables over NVLink while Q is projected
+            ops.linear_tc(h, w_in[128:], b_in[128:], out0=kv[:n])
+            peer.barrier()                                   # every rank is done reading its previous halo rows
+            peer.push_forward(kv[:n])
+            ops.linear_tc(h, w_in[:128], b_in[:128], out0=qg[:, :128])
+            peer.barrier()                                   # all pushes have landed
         else:
             # K|V first, start the halo all-to-all, project Q while the rows travel
             ops.linear_tc(h, w_in[128:], b_in[128:], out0=kv[:n])
@@ -80,7 +96,7 @@ class _P2VGraphLayer(torch.autograd.Function):
         o, stats = ops.gat_fwd_raw(qg[:, :128], kv, graph, heads, p_drop, seed)
         emb = ops.linear_tc(o, w_o, b_o, ops.EPI_BIAS_SELECT, aux=h, rowptr=graph.rowptr)
         ctx.save_for_backward(x, z1, a1, a2, h, qg, kv, o, stats, mean, rstd, gamma, w0, w3, w5, w_in, w_o)
-        ctx.cfg = dict(cfg, count=count)
+        ctx.cfg = dict(cfg, count=count, kv_version=peer.version if peer is not None else 0)
         return emb
 
     @staticmethod
@@ -108,19 +124,29 @@ class _P2VGraphLayer(torch.autograd.Function):
             dkv = torch.empty(graph.n_cols, 256, dtype=F32, device=x.device)
             ops.gat_delta_raw(o, qg[:, 128:], heads, stats)
             ops.gat_bwd_src_raw(qg[:, :128], kv, graph, heads, p_drop, seed, qg[:, 128:], stats, dkv)
-            returned = torch.empty(plan.send_idx.numel(), 256, dtype=F32, device=x.device)
-            work = plan.reverse_exchange(dkv[n:], returned, async_op=True)
+            peer = plan.peer
+            if peer is not None:
+                if peer.version != cfg["kv_version"]:
+                    raise RuntimeError("p2v_graph_layer.backward: the symmetric K|V table was overwritten by a later forward "
+                                       "on the same HaloPlan; run backward before the next forward")
+                main = torch.cuda.current_stream()
+                peer.side.wait_stream(main)
+                with torch.cuda.stream(peer.side):           # partials travel while the dst-major pass runs
+                    peer.push_reverse(dkv)
+                    peer.barrier()
+                returned, work = peer.returned(), None
+            else:
+                returned = torch.empty(plan.send_idx.numel(), 256, dtype=F32, device=x.device)
+                work = plan.reverse_exchange(dkv[n:], returned, async_op=True)
             ops.gat_bwd_dst_raw(qg[:, :128], kv, graph, heads, p_drop, seed, o, qg[:, 128:], stats, dq)
             dw_q, db_q = ops.wgrad_tc(dq, h)
             w_in_t = w_in.t().contiguous()                                            # [128, 384]
             d_h = ops.linear_tc(dq, w_in_t[:, :128].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_rest)
             if work is not None:
                 work.wait()
-            off = 0
-            for cnt in plan.send_counts:      # fixed peer order, unique ids per peer: deterministic
-                if cnt:
-                    ops.rows_scatter_add_(dkv, plan.send_idx[off: off + cnt], returned[off: off + cnt])
-                off += cnt
+            if peer is not None:
+                torch.cuda.current_stream().wait_stream(peer.side)
+            ops.rows_reduce_peers_(dkv[:n], returned, plan.slot)      # one pass, fixed peer order: deterministic
             dw_kv, db_kv = ops.wgrad_tc(dkv[:n], h)
             dw_in, db_in = torch.cat([dw_q, dw_kv]), torch.cat([db_q, db_kv])
             d_h = ops.linear_tc(dkv[:n], w_in_t[:, 128:].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_h)
@@ -132,7 +158,7 @@ class _P2VGraphLayer(torch.autograd.Function):
         sums = ops.bn_bwd_reduce(d_y, z1, mean, rstd)
         world = 1
         if training:
-            sums, _ = _allreduce_sums(sums, 0, group, sync_bn)
+            sums, _ = _allreduce_sums(sums, 0, group, sync_bn, count)
             if sync_bn and dist.is_initialized():
                 world = dist.get_world_size(group)
         d_beta64, d_gamma64 = sums[0], sums[1]

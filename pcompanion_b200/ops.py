@@ -557,3 +557,15 @@ def rows_scatter_add_(table: torch.Tensor, index: torch.Tensor, rows: torch.Tens
     call("pc_rows_scatter_add", dev(rows.contiguous(), F32, "rows"), dev(index, I64, "index"), index.numel(),
          table.shape[1], dev(table, F32, "table"), stream())
     return table
+
+
+def rows_reduce_peers_(table: torch.Tensor, rows: torch.Tensor, slot: torch.Tensor) -> torch.Tensor:
+    """table[r] += sum_p rows[slot[p, r]] over the peers p in ascending order (slot < 0: nothing from p)."""
+    world, n = slot.shape
+    if table.shape[0] != n or not table.is_contiguous():
+        raise ValueError("rows_reduce_peers_: table must be a contiguous [n, width] tensor matching slot [world, n]")
+    if rows.numel() == 0:
+        return table
+    call("pc_rows_reduce_peers", dev(rows.contiguous(), F32, "rows"), dev(slot, I32, "slot"), world, n, table.shape[1],
+         dev(table, F32, "table"), stream())
+    return table

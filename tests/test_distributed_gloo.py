@@ -30,7 +30,7 @@ def _worker(rank, world, port, results):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import p2v, retrieval as oret
-        from pcompanion_b200.distributed import HaloPlan, allreduce_gradients
+        from pcompanion_b200.distributed import HaloPlan, allreduce_gradients, partition_edges
         n, rowptr, col, q, kv, d_o = _global_problem()
         bounds = [0, 30, n]                                         # uneven partition
         b0, b1 = bounds[rank], bounds[rank + 1]
@@ -59,6 +59,19 @@ def _worker(rank, world, port, results):
         dq_ref, dkv_ref = p2v.gat_csr_backward(q, kv, rowptr, col, 4, d_o)
         np.testing.assert_allclose(dq, dq_ref[b0:b1], rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(dkv_loc.numpy(), dkv_ref[b0:b1], rtol=1e-12, atol=1e-12)
+        # distributed CSR build: every rank starts from an arbitrary slice of the edge list (with duplicates)
+        erow = np.repeat(np.arange(n), np.diff(rowptr)); ecol = col.astype(np.int64)
+        perm = np.random.default_rng(5).permutation(erow.size)
+        erow, ecol = np.concatenate([erow[perm], erow[:17]]), np.concatenate([ecol[perm], ecol[:17]])
+        mine = slice(rank, None, world)
+        prow, pcol = partition_edges(torch.tensor(erow[mine]), torch.tensor(ecol[mine]), bounds, rank)
+        assert np.array_equal(prow.numpy(), lp) and np.array_equal(pcol.numpy(), lcol)
+        # row-fetch plan (triplet positives / negatives owned by other ranks): rowptr=None
+        ids = torch.tensor(np.random.default_rng(7 + rank).integers(0, n, 40))
+        fetch = HaloPlan(None, ids, bounds, rank)
+        got = torch.empty(fetch.n_halo, kv.shape[1], dtype=kv_loc.dtype)
+        fetch.forward_exchange(kv_loc[fetch.send_idx].contiguous(), got)
+        assert np.array_equal(torch.cat([kv_loc, got])[fetch.col_ext].numpy(), kv[ids.numpy()])
         # replicated-weight gradient all-reduce
         lin = torch.nn.Linear(4, 3)
         for p in lin.parameters():

@@ -168,3 +168,46 @@ def test_full_size_c4_retrieval_properties():
     parts = [CatalogIndex(cat[a:b], tid[a:b], index_base=a, num_types=t).topk(q, k, rt) for a, b in zip(bounds[:-1], bounds[1:])]
     ms, mi = ops.topk_merge(torch.cat([x[0] for x in parts], 1), torch.cat([x[1] for x in parts], 1), k)
     assert torch.equal(mi, i) and torch.equal(ms, s)
+
+
+def test_c3_pcompanion_joint_step_on_1m_catalog_matches_torch_port():
+    """BASELINE config C3 at full size: 1 M-product frozen table, the reference's NUM_TYPES = 34,800 (config.py:27),
+    batch 256 (config.py:31): forward, 0.8 item + 0.2 type loss, backward and one Adam step against the torch-CPU
+    port of p_companion.py carrying the same weights."""
+    from oracle.torch_port import PortPCompanion
+    from pcompanion_b200 import PCompanion
+    p, t, b = 1_000_000, 34_800, 256
+    cfg = make_cfg(NUM_TYPES=t)
+    g = torch.Generator().manual_seed(3)
+    table = torch.randn(p, 128, generator=g)
+    torch.manual_seed(5)
+    ours = PCompanion(cfg, table)
+    port = PortPCompanion(cfg, table)
+    port.load_state_dict(ours.state_dict())                       # same key names as the reference
+    ours = ours.to(dev()).train(); port.train()
+    batch = {"query_ids": torch.randint(0, p, (b,), generator=g), "query_types": torch.randint(0, t, (b,), generator=g),
+             "positive_types": torch.randint(0, t, (b, 1), generator=g), "negative_types": torch.randint(0, t, (b, 1), generator=g),
+             "positive_items": torch.randn(b, 128, generator=g), "negative_items": torch.randn(b, 128, generator=g)}
+    dbatch = {k: v.to(dev()) for k, v in batch.items()}
+    opt_o = torch.optim.Adam([q for q in ours.parameters() if q.requires_grad], lr=1e-3)
+    opt_p = torch.optim.Adam([q for q in port.parameters() if q.requires_grad], lr=1e-3)
+    out = ours(dbatch)
+    loss = ours.compute_loss(dbatch, out)
+    loss.backward()
+    ref = port(batch["query_ids"], batch["query_types"])
+    ref_loss = port.loss(ref, batch["positive_types"].squeeze(-1), batch["negative_types"].squeeze(-1),
+                         batch["positive_items"], batch["negative_items"])
+    ref_loss.backward()
+    close(out["type_similarities"], ref["type_similarities"].detach().numpy(), what="type_similarities")
+    assert torch.equal(out["complementary_types"].cpu(), ref["complementary_types"])
+    close(out["projected_embeddings"], ref["projected_embeddings"].detach().numpy(), what="projected")
+    close(loss, ref_loss.detach().numpy(), what="loss")
+    refp = dict(port.named_parameters())
+    for k, v in ours.named_parameters():
+        if v.requires_grad:
+            close(v.grad, refp[k].grad.numpy(), rel=5e-5, atol=1e-9, what="grad " + k)
+    opt_o.step(); opt_p.step()
+    for k, v in ours.named_parameters():
+        if v.requires_grad:
+            close(v, refp[k].detach().numpy(), rel=5e-5, what="param after Adam " + k)
+    assert not ours.product_embeddings.weight.requires_grad          # frozen table, p_companion.py:26
