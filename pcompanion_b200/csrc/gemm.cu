@@ -6,9 +6,10 @@
 //
 // Precision: the reference computes these GEMMs in fp32 and BASELINE.json asks for 1e-5 relative
 // parity, which single-pass TF32/BF16 tensor-core math (~1e-3) cannot give.  Each operand is
-// therefore split on the fly into hi = rn_tf32(x) and lo = x - hi, and three tcgen05.mma
+// therefore split on the fly into hi = trunc_tf32(x) (what the tensor core reads of the raw
+// fp32 word anyway) and lo = rn_tf32(x - hi) (weights: hi = rn_tf32(w)), and three products
 // (kind::tf32, fp32 accumulation in TMEM) are issued per K step: lo.hi + hi.lo + hi.hi.
-// The dropped lo.lo term and the tf32 rounding of lo are ~2^-21 relative.  The tensor core
+// The dropped lo.lo term is < 2^-20 relative (2^-22 on average) and the rounding of lo 2^-21.  The tensor core
 // accumulates with truncation (measured: -2.4e-8 relative per MMA on same-sign data,
 // profiles/gemm_accuracy.py), so the hi.hi chain and the small cross terms go to two separate
 // TMEM accumulators (the cross terms would otherwise cost a truncation at the full magnitude
@@ -16,7 +17,7 @@
 //
 // Structure (one persistent CTA per SM, 512 threads, warp-specialised):
 //   warp 0      TMA producer: A [128 x 32] and W [bn x 32] fp32 tiles, 128-byte swizzle, 3 stages
-//   warps 8-15  split the landed tiles into hi (in place) / lo (second buffer) in shared memory
+//   warps 8-15  compute the lo tiles of the landed activation tiles (the raw tile itself is the hi operand)
 //   warp 1      one elected lane issues the tcgen05.mma triple per K step; tcgen05.commit frees stages
 //   warps 4-7   epilogue: tcgen05.ld both accumulators (double-buffered in TMEM), bias / tanh /
 //               tanh-gradient / row-select, 128-byte row segments straight to global memory
@@ -33,7 +34,7 @@ namespace {
 constexpr int MAX_BN = 128;             // columns per tile: 2 accumulators x 2 buffers x 128 = the 512 TMEM columns
 constexpr int A_BYTES = BM * BK * 4;    // 16 KB
 constexpr int B_BYTES = MAX_BN * BK * 4;  // 16 KB
-constexpr int A_STAGES = 4;             // activation tiles come from HBM: deep ring (raw tile becomes the hi tile in place)
+constexpr int A_STAGES = 4;             // activation tiles come from HBM: deep ring (the raw tile is the hi operand)
 constexpr int LO_STAGES = 2;            // lo tiles of A live only between the split and the MMA
 constexpr int B_STAGES = 3;             // weight tiles (pre-split hi | lo) come from L2
 constexpr int OFF_LO = A_STAGES * A_BYTES;
@@ -171,6 +172,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t idesc = instr_desc_tf32(p.bn);
+    // full-width tiles: W_hi and W_lo sit back to back in the stage and so do the two accumulators, so
+    // a_hi . [W_hi | W_lo] is ONE 256-wide MMA (a_hi is fetched from shared memory once instead of twice)
+    const bool wide = p.bn == MAX_BN;
+    const uint32_t idesc_wide = instr_desc_tf32(2 * MAX_BN);
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
@@ -188,9 +193,14 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t adv = uint64_t(kk * 32 >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle row
-            umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | kk) != 0);
-            umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
+            if (wide) {
+              umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc_wide, (kb | kk) != 0);   // main | cross = a_hi . [W_hi | W_lo]
+              umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, 1);
+            } else {
+              umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | kk) != 0);
+              umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
+              umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
+            }
           }
           umma_commit(a_empty + 8 * ra.stage);
           umma_commit(lo_empty + 8 * rl.stage);
@@ -208,7 +218,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
   } else if (warp >= 8) {
-    // ---------------- activation split: hi = rn_tf32(x) in place, lo = x - hi into the lo ring
+    // ---------------- activation split.  The raw fp32 tile IS the hi operand: under kind::tf32 the tensor core
+    // ignores the low 13 mantissa bits, so hi = trunc_tf32(x) needs no rewrite; only lo = rn_tf32(x - hi) is
+    // written (to the lo ring).  x = hi + (x - hi) exactly and |lo| < 2^-10 |x|.
     Ring<A_STAGES> ra;
     Ring<LO_STAGES> rl;
     Ring<B_STAGES> rb;
@@ -240,10 +252,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int it = 0; it < A_BYTES / 16 / SPLIT_THREADS; ++it) v[it] = lds128(hi_base + (tid + it * SPLIT_THREADS) * 16);
 #pragma unroll
         for (int it = 0; it < A_BYTES / 16 / SPLIT_THREADS; ++it) {
-          float4 h, l;
-          h.x = to_tf32(v[it].x); h.y = to_tf32(v[it].y); h.z = to_tf32(v[it].z); h.w = to_tf32(v[it].w);
-          l.x = to_tf32(v[it].x - h.x); l.y = to_tf32(v[it].y - h.y); l.z = to_tf32(v[it].z - h.z); l.w = to_tf32(v[it].w - h.w);
-          sts128(hi_base + (tid + it * SPLIT_THREADS) * 16, h);
+          float4 l;
+          l.x = to_tf32(v[it].x - trunc_tf32(v[it].x)); l.y = to_tf32(v[it].y - trunc_tf32(v[it].y));
+          l.z = to_tf32(v[it].z - trunc_tf32(v[it].z)); l.w = to_tf32(v[it].w - trunc_tf32(v[it].w));
           sts128(lo_base + (tid + it * SPLIT_THREADS) * 16, l);
         }
         fence_proxy_async();
@@ -346,14 +357,16 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // accumulators (hi.hi and cross terms) are added, rounded, into the CTA's fp32 partial in
 // global memory.  A second kernel sums the partials in CTA order (deterministic, no atomics).
 constexpr int WG_ROWS = 16;                        // reduction rows per stage (2 x UMMA_K)
-constexpr int WG_STAGES = 6;                       // raw tiles from HBM (they become the hi tiles in place)
-constexpr int WG_LO_STAGES = 2;                    // lo tiles live only between the split and the MMA
+constexpr int WG_STAGES = 4;                       // a stage = raw dY | lo dY | raw X | lo X.  The raw tiles are the hi
+                                                   // operands as they are (the tensor core ignores the low 13 mantissa
+                                                   // bits); the lo tiles are written next to them by the split warps, so
+                                                   // the only ring is TMA -> split -> MMA -> free (profiles/r1_gemm_stage_probe.md)
 constexpr int WG_MAX_K = 256;
 constexpr int WG_DY_BYTES = BM * WG_ROWS * 4;      // 8 KB: 128 columns x 16 rows
 constexpr int WG_X_BYTES = WG_MAX_K * WG_ROWS * 4; // 16 KB
-constexpr int WG_STAGE_BYTES = WG_DY_BYTES + WG_X_BYTES;           // 24 KB
-constexpr int WG_OFF_LO = WG_STAGES * WG_STAGE_BYTES;
-constexpr int WG_SMEM = (WG_STAGES + WG_LO_STAGES) * WG_STAGE_BYTES + 1024 + SMEM_MISC;   // 192 KB + misc
+constexpr int WG_OFF_X = 2 * WG_DY_BYTES;          // raw X starts here; its lo tile follows at + k * WG_ROWS * 4
+constexpr int WG_STAGE_BYTES = 2 * (WG_DY_BYTES + WG_X_BYTES);     // 48 KB
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + SMEM_MISC;   // 192 KB + misc
 constexpr int WG_GROUP_BYTES = WG_ROWS * 128;      // one 32-column group of a stage
 constexpr int WG_FLUSH = 32;                       // blocks per accumulation chain
 
@@ -382,19 +395,17 @@ __device__ __forceinline__ uint32_t instr_desc_tf32_mn(int n) {
 }
 
 using WgPipe = Ring<WG_STAGES>;
-using WgLoPipe = Ring<WG_LO_STAGES>;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                     const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* misc = smem + (WG_STAGES + WG_LO_STAGES) * WG_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // full[6], ready[6], empty[6], lo_empty[2], tmem_full, tmem_empty
+  uint8_t* misc = smem + WG_STAGES * WG_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // full[S], ready[S], empty[S], lo_empty[L], tmem_full, tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
   const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + WG_STAGES), empty_bar = smem_u32(bars + 2 * WG_STAGES);
-  const uint32_t lo_empty_bar = smem_u32(bars + 3 * WG_STAGES);
-  const uint32_t tfull_bar = lo_empty_bar + 8 * WG_LO_STAGES, tempty_bar = tfull_bar + 8;
+  const uint32_t tfull_bar = smem_u32(bars + 3 * WG_STAGES), tempty_bar = tfull_bar + 8;
   const int warp = warp_id(), lane = lane_id();
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
@@ -402,7 +413,6 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
       mbar_init(ready_bar + 8 * s, SPLIT_THREADS / 32);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    for (int s = 0; s < WG_LO_STAGES; ++s) mbar_init(lo_empty_bar + 8 * s, 1);
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -430,15 +440,18 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
         uint8_t* st = smem + pipe.stage * WG_STAGE_BYTES;
         mbar_arrive_expect_tx(full_bar + 8 * pipe.stage, WG_DY_BYTES + x_bytes);
         tma_load_3d(smem_u32(st), &map_dy, 0, row0, half * 4, full_bar + 8 * pipe.stage);
-        tma_load_3d(smem_u32(st + WG_DY_BYTES), &map_x, 0, row0, 0, full_bar + 8 * pipe.stage);
+        tma_load_3d(smem_u32(st + WG_OFF_X), &map_x, 0, row0, 0, full_bar + 8 * pipe.stage);
         pipe.advance();
       }
     }
   } else if (warp == 1) {
     WgPipe pipe;
-    WgLoPipe lo;
     const uint32_t idesc = instr_desc_tf32_mn(p.k);
-    const uint32_t d_main = tmem_base, d_cross = tmem_base + WG_MAX_K;
+    // k <= 128: X_hi | X_lo (adjacent in the stage) form ONE operand of width 2k and main | cross are adjacent in
+    // TMEM, so dY_hi . [X_hi | X_lo] is a single MMA (dY_hi is fetched from shared memory once instead of twice)
+    const bool wide = 2 * p.k <= 256;
+    const uint32_t idesc_wide = instr_desc_tf32_mn(2 * p.k);
+    const uint32_t d_main = tmem_base, d_cross = tmem_base + uint32_t(p.k);
     uint32_t flush_phase = 0;
     for (int64_t i = 0; i < my_blocks; ++i) {
       const int in_chain = int(i % WG_FLUSH);
@@ -450,55 +463,55 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
       tc_fence_after();
       if (lane == 0) {
         const uint32_t st = smem_u32(smem + pipe.stage * WG_STAGE_BYTES);
-        const uint32_t sl = smem_u32(smem + WG_OFF_LO + lo.stage * WG_STAGE_BYTES);
 #pragma unroll
         for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
-          const uint64_t a_hi = smem_desc_mn_sw128(st + ks * 1024), a_lo = smem_desc_mn_sw128(sl + ks * 1024);
-          const uint64_t b_hi = smem_desc_mn_sw128(st + WG_DY_BYTES + ks * 1024);
-          const uint64_t b_lo = smem_desc_mn_sw128(sl + WG_DY_BYTES + ks * 1024);
+          const uint64_t a_hi = smem_desc_mn_sw128(st + ks * 1024), a_lo = smem_desc_mn_sw128(st + WG_DY_BYTES + ks * 1024);
+          const uint64_t b_hi = smem_desc_mn_sw128(st + WG_OFF_X + ks * 1024);
+          const uint64_t b_lo = smem_desc_mn_sw128(st + WG_OFF_X + x_bytes + ks * 1024);
           const uint32_t accum = (in_chain | ks) != 0;
-          umma_tf32(d_cross, a_lo, b_hi, idesc, accum);
-          umma_tf32(d_cross, a_hi, b_lo, idesc, 1);
-          umma_tf32(d_main, a_hi, b_hi, idesc, accum);
+          if (wide) {
+            umma_tf32(d_main, a_hi, b_hi, idesc_wide, accum);     // main | cross = dY_hi . [X_hi | X_lo]
+            umma_tf32(d_cross, a_lo, b_hi, idesc, 1);
+          } else {
+            umma_tf32(d_cross, a_lo, b_hi, idesc, accum);
+            umma_tf32(d_cross, a_hi, b_lo, idesc, 1);
+            umma_tf32(d_main, a_hi, b_hi, idesc, accum);
+          }
         }
         umma_commit(empty_bar + 8 * pipe.stage);
-        umma_commit(lo_empty_bar + 8 * lo.stage);
         if (in_chain == WG_FLUSH - 1 || i == my_blocks - 1) umma_commit(tfull_bar);
       }
       __syncwarp();
       if (in_chain == WG_FLUSH - 1) flush_phase ^= 1;
       pipe.advance();
-      lo.advance();
     }
   } else if (warp >= 8) {
     // split hi/lo; a thread owns one (32-column group, 16-byte chunk, 8-row half) item of dY or X, so the dY
     // column sums stay in its registers
     WgPipe pipe;
-    WgLoPipe lo;
     const int tid = threadIdx.x - 256;
     const int dy_items = (BM / 4) * 2, x_items = (p.k / 4) * 2;   // 64 + up to 128 <= 256 threads
     const bool active = tid < dy_items + x_items;
     const bool is_dy = tid < dy_items;
     const int item = is_dy ? tid : tid - dy_items;
-    const int pair = item >> 1, r0 = (item & 1) * 8;
-    const int c = pair & 7;
-    const uint32_t op_off = (is_dy ? 0u : uint32_t(WG_DY_BYTES)) + uint32_t(pair >> 3) * WG_GROUP_BYTES;
+    // lane -> 16-byte chunk c of a 128-byte row: the 8 lanes of a quarter-warp cover one whole row (no bank conflicts)
+    const int c = item & 7, r0 = ((item >> 3) & 1) * 8, group = item >> 4;
+    const uint32_t op_off = (is_dy ? 0u : uint32_t(WG_OFF_X)) + uint32_t(group) * WG_GROUP_BYTES;
+    const uint32_t lo_off = is_dy ? uint32_t(WG_DY_BYTES) : x_bytes;     // the lo tile sits right behind its raw tile
     float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t i = 0; i < my_blocks; ++i) {
       mbar_wait(full_bar + 8 * pipe.stage, pipe.phase);
-      mbar_wait(lo_empty_bar + 8 * lo.stage, lo.phase ^ 1);
       if (active) {
         const uint32_t base = smem_u32(smem + pipe.stage * WG_STAGE_BYTES + op_off);
-        const uint32_t lo_base = smem_u32(smem + WG_OFF_LO + lo.stage * WG_STAGE_BYTES + op_off);
+        const uint32_t lo_base = base + lo_off;
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
           const int r = r0 + rr;
           const uint32_t off = uint32_t(r * 128 + (((((c >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4));
           const float4 v = lds128(base + off);
-          float4 h, l;
-          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-          l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-          sts128(base + off, h);
+          float4 l;
+          l.x = to_tf32(v.x - trunc_tf32(v.x)); l.y = to_tf32(v.y - trunc_tf32(v.y));
+          l.z = to_tf32(v.z - trunc_tf32(v.z)); l.w = to_tf32(v.w - trunc_tf32(v.w));
           sts128(lo_base + off, l);
           colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w;
         }
@@ -507,11 +520,10 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(ready_bar + 8 * pipe.stage);
       pipe.advance();
-      lo.advance();
     }
     if (p.partial_b && is_dy) {
       // logical chunk c of group g covers columns g*32 + 4c .. +3 (the swizzle only permutes positions)
-      float* dst = p.partial_b + int64_t(subset * 2 + (item & 1)) * p.n + half * BM + (pair >> 3) * 32 + c * 4;
+      float* dst = p.partial_b + int64_t(subset * 2 + ((item >> 3) & 1)) * p.n + half * BM + group * 32 + c * 4;
       *reinterpret_cast<float4*>(dst) = colsum;
     }
   } else if (warp >= 4) {
@@ -529,7 +541,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
       for (int c0 = 0; c0 < p.k; c0 += 32) {
         uint32_t r[32], rc[32];
         tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(WG_MAX_K + c0), rc);
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(p.k + c0), rc);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 v = make_float4(__uint_as_float(r[j]) + __uint_as_float(rc[j]), __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]),

@@ -99,6 +99,9 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// What the tensor core itself keeps of an fp32 operand under kind::tf32: the low 13 mantissa bits are ignored.
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 // K-major operand tile, 128-byte swizzle, rows of 128 bytes, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
   return uint64_t((addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
