@@ -297,17 +297,13 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
   }
   PC_RING_ISSUE_QG(RING)
   const float scale_log2e = scale * LOG2E;
-  float4 k_next = ldg4(KV + c0 * KV4 + lane), v_next = ldg4(KV + c0 * KV4 + ROW4 + lane);
   for (int r = 0; r < cols; ++r) {
     const int64_t j = c0 + r;
     const int beg = __shfl_sync(FULL, my_rel, r), end = __shfl_sync(FULL, my_rel, r + 1);
     float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
-    const float4 k = k_next, v = v_next;
-    if (r + 1 < cols) {                                   // the next column's own K|V row arrives while this one is processed
-      k_next = ldg4(KV + (j + 1) * KV4 + lane);
-      v_next = ldg4(KV + (j + 1) * KV4 + ROW4 + lane);
-    }
     if (end > beg) {
+      const float4 k = ldg4(KV + j * KV4 + lane);
+      const float4 v = ldg4(KV + j * KV4 + ROW4 + lane);
       for (int base = beg; base < end; base += 32) {
         const int cnt = min(32, end - base);
         int my_row = 0;
@@ -407,7 +403,7 @@ int check_common(const void* a, const void* b, const void* c, const void* d, int
     default: { constexpr int H = 8; constexpr bool DROP = DROPV; CALL; } break; \
   }
 
-constexpr int RU_FWD = 2, RU_DST = 2, RU_SRC = 2;   // edges per arithmetic batch in the ring kernels (data is already in shared memory)
+constexpr int RU_FWD = 3, RU_DST = 3, RU_SRC = 2;   // edges per arithmetic batch in the ring kernels (data is already in shared memory)
 
 }  // namespace
 }  // namespace pc

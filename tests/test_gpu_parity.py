@@ -186,6 +186,84 @@ def test_gat_forward_backward_matches_oracle(heads):
     assert (o[::7] == 0).all()                                   # empty rows
 
 
+@pytest.mark.parametrize("n_dst", [1, 3, 4, 5, 9, 64])
+def test_gat_ring_edge_cases_degrees_and_chunk_tails(n_dst):
+    """The kernels prefetch 8 rows ahead across the rows of a 4-row chunk: degrees 0, 1, around the ring depth,
+    around the 32-entry id window, and far beyond both; row counts around the chunk size; separate (unpacked) Q / dO."""
+    from pcompanion_b200 import ops
+    from oracle import p2v
+    rng = np.random.default_rng(100 + n_dst)
+    n_src = 1500
+    degs = [0, 1, 7, 8, 9, 31, 32, 33, 100, 1000, 2, 0, 0, 17]
+    deg = np.array([degs[(i * 5 + n_dst) % len(degs)] for i in range(n_dst)])
+    rowptr = np.zeros(n_dst + 1, np.int64); np.cumsum(deg, out=rowptr[1:])
+    col = np.concatenate([np.sort(rng.choice(n_src, d, replace=False)) for d in deg] + [np.zeros(0, np.int64)]).astype(np.int32)
+    q = rng.normal(size=(n_dst, 128)).astype(np.float32)
+    kv = rng.normal(size=(n_src, 256)).astype(np.float32)
+    d_o = rng.normal(size=(n_dst, 128)).astype(np.float32)
+    graph = ops.CSRGraph(torch.tensor(rowptr, device=dev()), torch.tensor(col, device=dev()), n_dst, n_src)
+    for heads in (1, 4):
+        qt = torch.tensor(q, device=dev(), requires_grad=True)
+        kvt = torch.tensor(kv, device=dev(), requires_grad=True)
+        o = ops.gat_attention(qt, kvt, graph, heads)
+        o.backward(torch.tensor(d_o, device=dev()))
+        ro, _ = p2v.gat_csr_forward(q.astype(np.float64), kv.astype(np.float64), rowptr, col, heads)
+        rdq, rdkv = p2v.gat_csr_backward(q.astype(np.float64), kv.astype(np.float64), rowptr, col, heads, d_o.astype(np.float64))
+        # atol: a row with one neighbour has softmax weight 1 and a mathematically zero dq (rounding noise on both sides)
+        close(o, ro, what=f"o h{heads}", atol=1e-6)
+        close(qt.grad, rdq, what=f"dq h{heads}", atol=1e-6)
+        close(kvt.grad, rdkv, what=f"dkv h{heads}", atol=1e-6)
+        a = ops.gat_attention(qt.detach(), kvt.detach(), graph, heads, 0.3, 5)
+        b = ops.gat_attention(qt.detach(), kvt.detach(), graph, heads, 0.3, 5)
+        assert torch.equal(a, b)
+
+
+def test_halo_push_and_peer_reduction_kernels_on_one_gpu():
+    """pc_halo_push with two 'peers' that are both buffers of this GPU (gather + strided store semantics, cyclic start),
+    and pc_rows_reduce_peers against index_add in the same peer order."""
+    import ctypes
+    from pcompanion_b200 import ops
+    from pcompanion_b200._lib import call, dev as dptr, stream
+    g = torch.Generator(device=dev()).manual_seed(9)
+    table = torch.randn(500, 256, generator=g, device=dev())
+    idx = torch.randperm(500, generator=g, device=dev())[:300]
+    peers = [torch.zeros(400, 256, device=dev()), torch.zeros(400, 256, device=dev())]
+    off = (ctypes.c_int64 * 3)(0, 120, 300)
+    base = (ctypes.c_void_p * 2)(peers[0].data_ptr(), peers[1].data_ptr())
+    dst0 = (ctypes.c_int64 * 2)(10, 200)
+    for first in (0, 120, 299, 300):
+        for pbuf in peers:
+            pbuf.zero_()
+        call("pc_halo_push", dptr(table, torch.float32, "t"), 256, dptr(idx, torch.int64, "i"), 2, off, base, None, dst0, first,
+             256, stream())
+        assert torch.equal(peers[0][10:130], table[idx[:120]]) and torch.equal(peers[1][200:380], table[idx[120:]])
+        assert peers[0][:10].abs().sum() == 0 and peers[0][130:].abs().sum() == 0 and peers[1][:200].abs().sum() == 0
+    # contiguous runs (index = NULL), strided source
+    wide = torch.randn(500, 384, generator=g, device=dev())
+    src0 = (ctypes.c_int64 * 2)(5, 250)
+    for pbuf in peers:
+        pbuf.zero_()
+    call("pc_halo_push", ctypes.c_void_p(wide[:, 128:].data_ptr()), 384, None, 2, off, base, src0, dst0, 0, 256, stream())
+    assert torch.equal(peers[0][10:130], wide[5:125, 128:]) and torch.equal(peers[1][200:380], wide[250:430, 128:])
+    # owner-side reduction
+    n, world = 700, 3
+    tbl = torch.randn(n, 256, generator=g, device=dev())
+    ref = tbl.clone()
+    slot = torch.full((world, n), -1, dtype=torch.int32, device=dev())
+    chunks, o = [], 0
+    for p_ in range(world):
+        ids = torch.randperm(n, generator=g, device=dev())[: 100 + 150 * p_]
+        slot[p_, ids] = torch.arange(o, o + ids.numel(), dtype=torch.int32, device=dev())
+        chunks.append(ids); o += ids.numel()
+    rows = torch.randn(o, 256, generator=g, device=dev())
+    o = 0
+    for ids in chunks:                                   # same peer order => same rounding
+        ref[ids] += rows[o: o + ids.numel()]; o += ids.numel()
+    ops.rows_reduce_peers_(tbl, rows, slot)
+    assert torch.equal(tbl, ref)
+
+
+
 def test_gat_is_deterministic_and_dropout_is_consistent():
     from pcompanion_b200 import ops
     rng = np.random.default_rng(3)
