@@ -60,6 +60,48 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     return torch.tanh(y) if tanh else y
 
 
+class _TypeScoresTC(torch.autograd.Function):
+    """S = base . W^T for a wide type table (P-Companion's [B, L] x [L, T] scoring, p_companion.py:60-62, T = 34,800 by
+    default) on the tcgen05 kernel: column chunks of 768 straight into the strided [B, T] output; the last T % 32
+    columns are a small library GEMM.  The type loss does not differentiate through S (ops.type_hinge takes the
+    factors); if a caller does, the dense gradients are library GEMMs."""
+    CHUNK = 768
+
+    @staticmethod
+    def forward(ctx, base, weight):
+        base = base.contiguous()
+        weight = weight.contiguous()
+        b, t = base.shape[0], weight.shape[0]
+        out = torch.empty(b, t, dtype=torch.float32, device=base.device)
+        main = t - t % 32
+        for c0 in range(0, main, _TypeScoresTC.CHUNK):
+            c1 = min(c0 + _TypeScoresTC.CHUNK, main)
+            ops.linear_tc(base, weight[c0:c1], None, out0=out[:, c0:c1])
+        if main < t:
+            out[:, main:] = base @ weight[main:].t()
+        ctx.save_for_backward(base, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        base, weight = ctx.saved_tensors
+        d_base = d_out @ weight if ctx.needs_input_grad[0] else None
+        d_w = d_out.t() @ base if ctx.needs_input_grad[1] else None
+        return d_base, d_w
+
+
+def type_scores(base: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """[B, L] x [T, L]^T -> [B, T].  Large batches run on the tensor-core kernel; below 16,384 rows the 2 * T / 768 launches
+    cost more than the GEMM and a single library call is used."""
+    if not base.is_cuda:
+        raise RuntimeError(f"pcompanion_b200.dense.type_scores: input on {base.device}; CUDA only (no CPU fallback)")
+    k = base.shape[1]
+    if base.dtype == torch.float32 and base.shape[0] >= 16384 and k % 32 == 0 and k <= 256 and weight.shape[0] >= 1024 \
+            and (weight.shape[0] * 4) % 16 == 0:
+        return _TypeScoresTC.apply(base, weight)
+    return F.linear(base, weight, None)
+
+
 def in_projection(h_query: torch.Tensor, h_kv: torch.Tensor, w: torch.Tensor, b: torch.Tensor):
     """Packed in-projection of nn.MultiheadAttention for query != key, key is value
     (torch F._in_projection_packed): Q from rows [0:E] of in_proj_weight, K|V from rows [E:3E]."""

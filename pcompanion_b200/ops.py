@@ -440,8 +440,52 @@ class _HingeType(torch.autograd.Function):
         return d, None, None, None
 
 
+class _HingeTypeFactored(torch.autograd.Function):
+    """Same loss value as _HingeType on S = base . W^T, but the gradient goes straight to the factors: only two
+    entries per row of S carry gradient, so d_base = c_i (W[neg_i] - W[pos_i]) and dW gets +-c_i base_i on two rows per
+    sample - no dense [B, T] gradient and none of the two [B, T]-sized backward GEMMs (they dominate C3).
+    dW is accumulated without float atomics: slots sorted by type (pc_sort_keys), summed per type in slot order."""
+
+    @staticmethod
+    def forward(ctx, base, weight, sims, pos, neg, margin: float):
+        sims = sims.contiguous()
+        pos, neg = pos.contiguous().to(I64), neg.contiguous().to(I64)
+        rows, nt = sims.shape
+        per = torch.empty(rows, dtype=F32, device=sims.device)
+        loss = torch.empty((), dtype=F32, device=sims.device)
+        call("pc_hinge_type_fwd", dev(sims, F32, "sims"), dev(pos, I64, "pos"), dev(neg, I64, "neg"), rows, nt, margin,
+             dev(per, F32, "per"), dev(loss, F32, "loss"), stream())
+        ctx.save_for_backward(base, weight, per, pos, neg)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        base, weight, per, pos, neg = ctx.saved_tensors
+        rows, nt = base.shape[0], weight.shape[0]
+        coef = torch.where((per > 0) & (pos != neg), g.to(F32) / rows, torch.zeros((), dtype=F32, device=per.device))
+        d_base = d_w = None
+        if ctx.needs_input_grad[0]:
+            d_base = coef.unsqueeze(1) * (weight[neg] - weight[pos])
+        if ctx.needs_input_grad[1]:
+            contrib = coef.unsqueeze(1) * base                                   # [B, L]
+            vals = torch.cat([-contrib, contrib]).contiguous()                   # slot i: pos_i, slot B + i: neg_i
+            slots = 2 * rows
+            keys = pack_keys(torch.cat([pos, neg]).to(I32), torch.arange(slots, dtype=I32, device=base.device))
+            type_bytes = max(1, ((max(nt, 2) - 1).bit_length() + 7) // 8)
+            sort_keys_(keys, ((1 << type_bytes) - 1) << 4)                       # stable: slots stay ascending inside a type
+            rowptr, col = csr_from_sorted_keys(keys, nt)
+            d_w = torch.empty(nt, base.shape[1], dtype=F32, device=base.device)
+            call("pc_rows_segment_sum", dev(vals, F32, "rows"), dev(rowptr, I64, "rowptr"), dev(col, I32, "col"), nt,
+                 base.shape[1], dev(d_w, F32, "out"), stream())
+        return d_base, d_w, None, None, None, None
+
+
 def type_hinge(sims, pos, neg, margin: float) -> torch.Tensor:
-    """mean clamp(margin - S[i,pos_i] + S[i,neg_i], 0)  (p_companion.py:95-103)."""
+    """mean clamp(margin - S[i,pos_i] + S[i,neg_i], 0)  (p_companion.py:95-103).  When `sims` was produced by
+    PCompanion.forward it carries its factors (base [B, L], W [T, L]) and the gradient bypasses the [B, T] matrix."""
+    factors = getattr(sims, "_pc_factors", None)
+    if factors is not None and factors[0].shape[0] == sims.shape[0] and factors[1].shape[0] == sims.shape[1]:
+        return _HingeTypeFactored.apply(factors[0], factors[1], sims.detach(), pos, neg, float(margin))
     return _HingeType.apply(sims, pos, neg, float(margin))
 
 

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .dense import linear
+from .dense import linear, type_scores
 
 
 class ComplementaryTypeTransition(nn.Module):
@@ -81,7 +81,10 @@ class PCompanion(nn.Module):
         query_embeddings = self.product_embeddings(self._query_indices(batch["query_ids"]))
         query_type_emb = self.query_type_embeddings(batch["query_types"])
         comp_base = self.type_transition(query_type_emb)
-        similarities = linear(comp_base, self.complementary_type_embeddings.weight, None)   # [B, T]
+        similarities = type_scores(comp_base, self.complementary_type_embeddings.weight)     # [B, T]
+        # the type loss reads two entries per row of this matrix; it takes its gradient path through the factors
+        # (ops.type_hinge), so the dense [B, T] backward only runs if a caller differentiates the matrix itself
+        similarities._pc_factors = (comp_base, self.complementary_type_embeddings.weight)
         _, top_types = ops.topk_rows(similarities.detach(), self.config.NUM_COMP_TYPES)
         comp_type_embeddings = self.complementary_type_embeddings(top_types)
         projected_embeddings = self.item_prediction(query_embeddings, comp_type_embeddings)
