@@ -46,8 +46,6 @@ constexpr int GEMM_THREADS = 512;
 constexpr int SPLIT_THREADS = 256;      // warps 8-15
 constexpr int SMEM_MISC = 4096;         // barriers, tmem pointer, bias
 constexpr int GEMM_SMEM = OPERAND_BYTES + 1024 + SMEM_MISC;
-constexpr int STAGES = 3;               // (wgrad kernel's ring depth is defined separately below)
-constexpr int STAGE_BYTES = 0;          // unused by the forward kernel
 
 enum Epilogue { EPI_BIAS = 0, EPI_BIAS_TANH = 1, EPI_TANH_GRAD = 2, EPI_BIAS_SELECT = 3, EPI_BIAS_ADD = 4 };
 
@@ -61,7 +59,6 @@ struct LinearParams {
   int epilogue;
   const float* aux; int ld_aux;      // EPI_TANH_GRAD: tanh output t (y = acc * (1 - t^2)); EPI_BIAS_SELECT: fallback rows
   const int64_t* rowptr;             // EPI_BIAS_SELECT: row keeps acc + bias iff rowptr[r+1] > rowptr[r]
-  int bsplit;                        // 1: the weight tile is loaded raw and split in the kernel (less L2 -> SM traffic)
 };
 
 // w_hi = rn_tf32(w), w_lo = rn_tf32(w - w_hi): the weight operand is split once per call, not once per tile
@@ -78,7 +75,7 @@ __global__ void split_tf32_kernel(const float4* __restrict__ w, int64_t n4, floa
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
-                     const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_wraw,
+                     const __grid_constant__ CUtensorMap map_wlo,
                      const __grid_constant__ CUtensorMap map_out0,
                      const __grid_constant__ CUtensorMap map_out1, const LinearParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -93,7 +90,6 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t lo_empty = smem_u32(bars + 3 * A_STAGES), b_full = smem_u32(bars + 3 * A_STAGES + LO_STAGES);
   const uint32_t b_empty = smem_u32(bars + 3 * A_STAGES + LO_STAGES + B_STAGES);
   const uint32_t tfull_bar = smem_u32(bars + 3 * A_STAGES + LO_STAGES + 2 * B_STAGES), tempty_bar = tfull_bar + 16;
-  const uint32_t b_ready = tempty_bar + 16;
   const int warp = warp_id(), lane = lane_id();
 
   if (threadIdx.x == 0) {
@@ -106,7 +102,6 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     for (int s = 0; s < B_STAGES; ++s) {
       mbar_init(b_full + 8 * s, 1);
       mbar_init(b_empty + 8 * s, 1);
-      mbar_init(b_ready + 8 * s, SPLIT_THREADS / 32);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
@@ -152,14 +147,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(b_empty + 8 * rb.stage, rb.phase ^ 1);
           uint8_t* st = smem + OFF_B + rb.stage * 2 * B_BYTES;
-          if (p.bsplit) {
-            mbar_arrive_expect_tx(b_full + 8 * rb.stage, b_tile_bytes);
-            tma_load_2d(smem_u32(st), &map_wraw, kb * BK, n0, b_full + 8 * rb.stage);
-          } else {
-            mbar_arrive_expect_tx(b_full + 8 * rb.stage, 2 * b_tile_bytes);
-            tma_load_2d(smem_u32(st), &map_whi, kb * BK, n0, b_full + 8 * rb.stage);
-            tma_load_2d(smem_u32(st + B_BYTES), &map_wlo, kb * BK, n0, b_full + 8 * rb.stage);
-          }
+          mbar_arrive_expect_tx(b_full + 8 * rb.stage, 2 * b_tile_bytes);
+          tma_load_2d(smem_u32(st), &map_whi, kb * BK, n0, b_full + 8 * rb.stage);
+          tma_load_2d(smem_u32(st + B_BYTES), &map_wlo, kb * BK, n0, b_full + 8 * rb.stage);
           rb.advance();
         }
       }
@@ -181,7 +171,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tc_fence_after();
       const uint32_t d_main = tmem_base + uint32_t(acc * 2 * MAX_BN), d_cross = d_main + MAX_BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait((p.bsplit ? b_ready : b_full) + 8 * rb.stage, rb.phase);
+        mbar_wait(b_full + 8 * rb.stage, rb.phase);
         mbar_wait(a_ready + 8 * ra.stage, ra.phase);
         tc_fence_after();
         if (lane == 0) {
@@ -223,26 +213,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // written (to the lo ring).  x = hi + (x - hi) exactly and |lo| < 2^-10 |x|.
     Ring<A_STAGES> ra;
     Ring<LO_STAGES> rl;
-    Ring<B_STAGES> rb;
     const int tid = threadIdx.x - 256;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       for (int kb = 0; kb < k_blocks; ++kb) {
-        if (p.bsplit) {   // weight tile: hi in place, lo right behind it
-          mbar_wait(b_full + 8 * rb.stage, rb.phase);
-          const uint32_t bh = smem_u32(smem + OFF_B + rb.stage * 2 * B_BYTES);
-          for (int i = tid; i < int(b_tile_bytes / 16); i += SPLIT_THREADS) {
-            const float4 v = lds128(bh + i * 16);
-            float4 h, l;
-            h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-            l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-            sts128(bh + i * 16, h);
-            sts128(bh + B_BYTES + i * 16, l);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_ready + 8 * rb.stage);
-          rb.advance();
-        }
         mbar_wait(a_full + 8 * ra.stage, ra.phase);
         mbar_wait(lo_empty + 8 * rl.stage, rl.phase ^ 1);
         const uint32_t hi_base = smem_u32(smem + ra.stage * A_BYTES);
@@ -619,11 +592,9 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
                                                                  reinterpret_cast<float4*>(w_hi), reinterpret_cast<float4*>(w_lo));
     PC_LAUNCH_CHECK();
   }
-  // measured (profiles/gemm_microbench.py): pre-split weights (0) beat the in-kernel split (1) by ~20 % - the
-  // operand-split warps sit on the critical path, the extra L2 -> SM traffic of the lo tile does not
-  p.bsplit = 0;
-  CUtensorMap map_a, map_whi, map_wlo, map_wraw;
-  if (int rc = make_map(&map_wraw, w, n, k, k, p.bn)) return rc;
+  // (splitting the weight tile inside the kernel instead was measured ~20 % slower: the operand-split warps sit on
+  // the critical path, the extra L2 -> SM traffic of the pre-split lo tile does not)
+  CUtensorMap map_a, map_whi, map_wlo;
   // consecutive K blocks of a row are adjacent in memory: let L2 fetch 256 B per miss so the next block's
   // request hits, halving the DRAM page activations of the strided [128 x 32] activation boxes
   if (int rc = make_map(&map_a, a, m, k, lda, BM, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return rc;
@@ -643,7 +614,7 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   }
   const int64_t tiles = ((m + BM - 1) / BM) * p.n_tiles;
   const int grid = int(tiles < sm_count() ? tiles : sm_count());
-  linear_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_wraw, map_out0, map_out1, p);
+  linear_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out0, map_out1, p);
   PC_LAUNCH_CHECK();
   return PC_OK;
 }
