@@ -209,27 +209,42 @@ class PeerHalo:
 
 
 class _HaloGather(torch.autograd.Function):
-    """[n_local, W] -> [n_local + n_halo, W]; backward returns the halo gradients to their owners."""
+    """[n_local, W] -> [n_local + n_halo, W]; backward returns the halo gradients to their owners.  Uses the plan's
+    peer-memory transport when it is enabled (``plan.enable_peer_memory(width=W)``), NCCL all-to-all otherwise."""
 
     @staticmethod
     def forward(ctx, table, plan: HaloPlan):
         table = table.contiguous()
         w = table.shape[1]
-        ext = torch.empty(plan.n_local + plan.n_halo, w, dtype=table.dtype, device=table.device)
-        ext[: plan.n_local].copy_(table)
-        send = ops.rows_gather(table, plan.send_idx)
-        plan.forward_exchange(send, ext[plan.n_local:])
-        ctx.plan = plan
+        peer = plan.peer if (plan.peer is not None and plan.peer.width == w) else None
+        if peer is not None:
+            ext = peer.table(plan.n_local + plan.n_halo)
+            ext[: plan.n_local].copy_(table)
+            peer.barrier()                       # the peers are done with the previous contents of their halo rows
+            peer.push_forward(table)
+            peer.barrier()
+            ctx.version = peer.version
+        else:
+            ext = torch.empty(plan.n_local + plan.n_halo, w, dtype=table.dtype, device=table.device)
+            ext[: plan.n_local].copy_(table)
+            send = ops.rows_gather(table, plan.send_idx)
+            plan.forward_exchange(send, ext[plan.n_local:])
+        ctx.plan, ctx.peer = plan, peer
         return ext
 
     @staticmethod
     def backward(ctx, d_ext):
-        plan = ctx.plan
+        plan, peer = ctx.plan, ctx.peer
         d_ext = d_ext.contiguous()
         w = d_ext.shape[1]
         d_local = d_ext[: plan.n_local].clone()
-        returned = torch.empty(plan.send_idx.numel(), w, dtype=d_ext.dtype, device=d_ext.device)
-        plan.reverse_exchange(d_ext[plan.n_local:].contiguous(), returned)
+        if peer is not None:
+            peer.push_reverse(d_ext)             # copy engines; every owner's run is contiguous
+            peer.barrier()
+            returned = peer.returned()
+        else:
+            returned = torch.empty(plan.send_idx.numel(), w, dtype=d_ext.dtype, device=d_ext.device)
+            plan.reverse_exchange(d_ext[plan.n_local:].contiguous(), returned)
         ops.rows_reduce_peers_(d_local, returned, plan.slot)          # fixed peer order: deterministic
         return d_local, None
 
@@ -329,6 +344,7 @@ def run_partitioned_bench(args, rank: int, world: int, dev: torch.device) -> Non
     trip_global = torch.cat([torch.randint(0, n_loc, (B.TRIPLETS, 1), generator=g, device=dev) + bounds[rank],
                              torch.randint(0, n_total, (B.TRIPLETS, 1 + B.KNEG), generator=g, device=dev)], dim=1)
     fetch = HaloPlan(None, trip_global.reshape(-1), bounds, rank)
+    fetch.enable_peer_memory(width=128)
     trip = fetch.col_ext.view_as(trip_global).contiguous()
     x_host, trip_host = x.cpu().pin_memory(), trip.cpu().pin_memory()
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()

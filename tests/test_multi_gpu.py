@@ -94,6 +94,8 @@ def _worker(rank, world, port, results):
         emb = forward_graph_partitioned(model2, torch.tensor(x[b0:b1], device=dev), plan)
         tr = torch.tensor(trips[rank], device=dev)
         fetch = HaloPlan(None, tr.reshape(-1), bounds, rank)
+        if transport == "peer push":
+            assert fetch.enable_peer_memory(width=128)
         ext = halo_gather(emb, fetch)
         te = fetch.col_ext.view_as(tr)
         loss = model2.triplet_loss_indexed(ext, te[:, 0], te[:, 1], te[:, 2:])
