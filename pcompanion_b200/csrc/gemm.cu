@@ -269,8 +269,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       if (p.epilogue == EPI_BIAS_SELECT && row < p.m) keep = p.rowptr[row + 1] > p.rowptr[row];
       for (int c0 = 0; c0 < p.bn; c0 += 32) {
         uint32_t r[32], rc[32];
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + c0), r);
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + MAX_BN + c0), rc);
+        tmem_ld32_async(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + c0), r);
+        tmem_ld32_async(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + MAX_BN + c0), rc);
+        tmem_ld_wait32(r);
+        tmem_ld_wait32(rc);
         const int n = n0 + c0;
         float y[32];
 #pragma unroll
@@ -527,8 +529,10 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
       tc_fence_after();
       for (int c0 = 0; c0 < p.k; c0 += 32) {
         uint32_t r[32], rc[32];
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(p.k + c0), rc);
+        tmem_ld32_async(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
+        tmem_ld32_async(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(p.k + c0), rc);
+        tmem_ld_wait32(r);
+        tmem_ld_wait32(rc);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 v = make_float4(__uint_as_float(r[j]) + __uint_as_float(rc[j]), __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]),

@@ -13,9 +13,11 @@
 // The approximate scores only have to find CANDIDATES - exactness comes from kernel 2 - so there is no
 // operand split: TMA lands fp32 tiles in shared memory and the tensor core reads them directly (it ignores
 // the low 13 mantissa bits).  A CTA owns one 128-row block (its query tile stays resident in shared memory)
-// and a contiguous range of product tiles ("unit") streamed through an 8-deep TMA ring; each epilogue thread
-// (= one score row) keeps a sorted list of the best KP candidates across the whole range; masked products
-// (type_id[p] != row_type[r]) never enter it.  Accumulators are quadruple-buffered in TMEM.
+// and a contiguous range of product tiles ("unit") streamed through a 7-deep TMA ring.  16 epilogue warps: a warp
+// reads its TMEM lane quarter (32 rows) for one 32-column chunk of every tile, so a thread scans 32 scores per tile
+// and keeps a sorted list of the best KP candidates of its (row, chunk) stream; masked products (type_id[p] !=
+// row_type[r]) never enter it - the type match is one shuffle + compare per product, the score is only looked at for
+// matches.  The warps never synchronise with each other.  Accumulators are quadruple-buffered in TMEM.
 // Kernel 2 (rescore_topk_kernel): one warp per row re-scores the candidates exactly (float64, sequential
 // over d - the score definition of retrieval.cu / oracle/retrieval.py), ranks them (score desc, index
 // asc) and checks the guard band: every product dropped by kernel 1 had an approximate score <= tau (the
@@ -32,13 +34,16 @@ namespace {
 constexpr int SC_BN = 128;              // products per tile
 constexpr int SC_TILE_BYTES = BM * BK * 4;          // one K block of a 128-row operand tile: 16 KB
 constexpr int SC_MAX_KB = 4;                        // dim <= 128
-constexpr int SC_B_STAGES = 8;
+constexpr int SC_B_STAGES = 7;
 constexpr int SC_OFF_B = SC_MAX_KB * SC_TILE_BYTES; // resident query tile first: 64 KB
-constexpr int SC_OPERAND_BYTES = SC_OFF_B + SC_B_STAGES * SC_TILE_BYTES;   // + 128 KB product ring = 192 KB
-constexpr int SC_THREADS = 256;
+constexpr int SC_OPERAND_BYTES = SC_OFF_B + SC_B_STAGES * SC_TILE_BYTES;   // + 112 KB product ring = 176 KB
+constexpr int SC_CHUNKS = 4;                        // 32-column chunks of a tile, one epilogue warp each per lane quarter
+constexpr int SC_EPI_THREADS = 128 * SC_CHUNKS;     // 16 epilogue warps: warp % 4 = TMEM lane quarter, warp / 4 = chunk
+constexpr int SC_THREADS = 128 + SC_EPI_THREADS;
 constexpr int SC_ACC = 4;                           // TMEM accumulator buffers (4 x 128 columns)
-constexpr int KP = 16;                              // candidates kept per (row, unit)
-constexpr int SC_LIST_BYTES = BM * KP * 8;          // per-row candidate lists (score, index) of the 128 epilogue threads
+constexpr int KP = 8;                               // candidates kept per (row, unit, chunk) list
+constexpr int SC_MAX_K = 16;                        // largest k (a row has at least 4 lists)
+constexpr int SC_LIST_BYTES = BM * SC_CHUNKS * KP * 8;   // candidate lists (score, index) of the 512 epilogue threads
 constexpr int SC_SMEM = SC_OPERAND_BYTES + SC_LIST_BYTES + 1024 + 4096;
 
 struct ScoreParams {
@@ -49,8 +54,8 @@ struct ScoreParams {
   int64_t tiles_per_unit;
   const int32_t* type_id;       // [products] or null
   const int32_t* row_type;      // [rows] or null (< 0: no restriction)
-  float* part_s;                // [rows, S, KP]
-  int32_t* part_i;              // [rows, S, KP] local product index, -1 = empty
+  float* part_s;                // [rows, S, SC_CHUNKS, KP]
+  int32_t* part_i;              // [rows, S, SC_CHUNKS, KP] local product index, -1 = empty
 };
 
 __global__ void __launch_bounds__(SC_THREADS, 1)
@@ -58,12 +63,11 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                        const ScoreParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* list_s = reinterpret_cast<float*>(smem + SC_OPERAND_BYTES);                     // [128][KP] scores
-  int32_t* list_i = reinterpret_cast<int32_t*>(smem + SC_OPERAND_BYTES + BM * KP * 4);   // [128][KP] indices
+  float* list_s = reinterpret_cast<float*>(smem + SC_OPERAND_BYTES);                                  // [128][4][KP] scores
+  int32_t* list_i = reinterpret_cast<int32_t*>(smem + SC_OPERAND_BYTES + BM * SC_CHUNKS * KP * 4);    // [128][4][KP] indices
   uint8_t* misc = smem + SC_OPERAND_BYTES + SC_LIST_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // q_full, q_empty, b_full[8], b_empty[8], tfull[4], tempty[4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
-  int32_t* types_s = reinterpret_cast<int32_t*>(misc + 512);   // [2][128] product types of the tile in flight
   const uint32_t q_full = smem_u32(bars + 0), q_empty = smem_u32(bars + 1);
   const uint32_t b_full = smem_u32(bars + 2), b_empty = b_full + 8 * SC_B_STAGES;
   const uint32_t tfull_bar = b_empty + 8 * SC_B_STAGES, tempty_bar = tfull_bar + 8 * SC_ACC;
@@ -78,7 +82,7 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
     for (int s = 0; s < SC_ACC; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
-      mbar_init(tempty_bar + 8 * s, 128);
+      mbar_init(tempty_bar + 8 * s, SC_EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -156,15 +160,18 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ---------------- epilogue: thread = one score row.  Its sorted candidate list (score desc, index asc) lives in
-    // shared memory; only the admission threshold stays in a register.  Per 32-score chunk an eligibility bit mask is
-    // built first (type match, above threshold), so the common case costs a few instructions per score.
+    // ---------------- epilogue: 16 warps.  Warp e = warp - 4 reads TMEM lane quarter e % 4 (rows 32 (e % 4) .. + 31)
+    // and owns the 32-column chunk e / 4 of every tile, so a thread scans 32 scores per tile and keeps its own sorted
+    // candidate list (score desc, index asc) in shared memory; a row's four lists are merged by the re-scoring
+    // kernel.  (With 4 warps scanning 128 scores each the epilogue took 3.4 us per tile against 1.4 us of TMA + MMA:
+    // one warp per scheduler cannot hide its own instruction latencies.)
     Ring<SC_ACC> ra;
-    const int quad = warp - 4;
+    const int e = warp - 4;
+    const int quad = e & 3, chunk = e >> 2;
     const int trow = quad * 32 + lane;
-    float* my_s = list_s + trow * KP;
-    int32_t* my_i = list_i + trow * KP;
-    int parity = 0;
+    const int c0 = chunk * 32;
+    float* my_s = list_s + (trow * SC_CHUNKS + chunk) * KP;
+    int32_t* my_i = list_i + (trow * SC_CHUNKS + chunk) * KP;
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
       const int m0 = int((u % m_blocks) * BM);
       const int range = int(u / m_blocks);
@@ -176,49 +183,44 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       for (int j = 0; j < KP; ++j) { my_s[j] = -INFINITY; my_i[j] = -1; }
       float thr = -INFINITY;          // weakest kept score once the list is full
       int kept = 0;
-      auto type_of = [&](int64_t tile) -> int {
-        const int64_t pidx = tile * SC_BN + trow;
+      auto type_of = [&](int64_t tile) -> int {   // lane j holds the type of product j of the warp's chunk of that tile
+        const int64_t pidx = tile * SC_BN + c0 + lane;
         return (tile < t_end && pidx < p.products) ? (p.type_id ? p.type_id[pidx] : 0) : -2;   // -2: past the catalog end
       };
       int t_next = type_of(t_beg);
       for (int64_t nt = t_beg; nt < t_end; ++nt) {
         const int64_t n0 = nt * SC_BN;
-        int32_t* ts = types_s + parity * SC_BN;
-        const uint32_t ts_addr = smem_u32(ts);
-        parity ^= 1;
-        ts[trow] = t_next;
-        t_next = type_of(nt + 1);      // in flight while this tile is processed
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int t_lane = t_next;
+        t_next = type_of(nt + 1);      // in flight while this tile is processed; the warps never synchronise with each other
         mbar_wait(tfull_bar + 8 * ra.stage, ra.phase);
         tc_fence_after();
-        for (int c0 = 0; c0 < SC_BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(ra.stage * SC_BN + c0), r);
-          uint32_t mask = 0;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(ra.stage * SC_BN + c0), r);
+        // bit j of mask: product j of the chunk is eligible for my row (exists and has my row's type)
+        const uint32_t valid = __ballot_sync(FULL, t_lane != -2);
+        uint32_t mask = 0;
+        if (__any_sync(FULL, rt >= 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mask |= uint32_t(__shfl_sync(FULL, t_lane, j) == rt) << j;   // rt >= 0 never equals -2
+        }
+        if (rt < 0) mask = valid;
+        if (row_ok && mask) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int t = lds32i(ts_addr + (c0 + j) * 4);
-            const bool e = t != -2 && (rt < 0 || t == rt) && (kept < KP || __uint_as_float(r[j]) > thr);
-            mask |= uint32_t(e) << j;
-          }
-          if (row_ok && mask) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (mask & (1u << j)) {
-                const float y = __uint_as_float(r[j]);
-                if (kept < KP || y > my_s[KP - 1]) {   // the threshold may have moved inside this chunk
-                  // insert keeping (score desc, index asc): indices arrive ascending, so an equal score goes after
-                  int pos = kept < KP ? kept : KP - 1;
-                  while (pos > 0 && my_s[pos - 1] < y) {
-                    my_s[pos] = my_s[pos - 1];
-                    my_i[pos] = my_i[pos - 1];
-                    --pos;
-                  }
-                  my_s[pos] = y;
-                  my_i[pos] = int32_t(n0 + c0 + j);
-                  if (kept < KP) ++kept;
-                  if (kept == KP) thr = my_s[KP - 1];
+            if (mask & (1u << j)) {
+              const float y = __uint_as_float(r[j]);
+              if (kept < KP || y > thr) {               // thr follows every insertion
+                // insert keeping (score desc, index asc): indices arrive ascending, so an equal score goes after
+                int pos = kept < KP ? kept : KP - 1;
+                while (pos > 0 && my_s[pos - 1] < y) {
+                  my_s[pos] = my_s[pos - 1];
+                  my_i[pos] = my_i[pos - 1];
+                  --pos;
                 }
+                my_s[pos] = y;
+                my_i[pos] = int32_t(n0 + c0 + j);
+                if (kept < KP) ++kept;
+                if (kept == KP) thr = my_s[KP - 1];
               }
             }
           }
@@ -228,8 +230,8 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         ra.advance();
       }
       if (row_ok) {
-        float* os = p.part_s + (row * p.units_per_block + range) * KP;
-        int32_t* oi = p.part_i + (row * p.units_per_block + range) * KP;
+        float* os = p.part_s + ((row * p.units_per_block + range) * SC_CHUNKS + chunk) * KP;
+        int32_t* oi = p.part_i + ((row * p.units_per_block + range) * SC_CHUNKS + chunk) * KP;
         for (int j = 0; j < KP; ++j) { os[j] = my_s[j]; oi[j] = my_i[j]; }
       }
     }
@@ -323,7 +325,7 @@ using namespace pc;
 
 extern "C" size_t pc_score_topk_workspace_bytes(int64_t rows, int units) {
   if (rows <= 0 || units <= 0) return 0;
-  return size_t(rows) * size_t(units) * KP * (sizeof(float) + sizeof(int32_t));
+  return size_t(rows) * size_t(units) * SC_CHUNKS * KP * (sizeof(float) + sizeof(int32_t));
 }
 
 extern "C" int pc_score_topk_dense(const float* q, int64_t rows, int dim, const float* catalog, int64_t products,
@@ -333,7 +335,7 @@ extern "C" int pc_score_topk_dense(const float* q, int64_t rows, int dim, const 
   PC_REQUIRE(rows >= 0 && products >= 0, PC_ERR_INVALID, "score_topk_dense: negative size");
   if (rows == 0) return PC_OK;
   PC_REQUIRE(q && catalog && out_scores && out_idx && flags && workspace, PC_ERR_INVALID, "score_topk_dense: null pointer");
-  PC_REQUIRE(k >= 1 && k <= KP, PC_ERR_UNSUPPORTED, "score_topk_dense: k=%d outside [1,%d]", k, KP);
+  PC_REQUIRE(k >= 1 && k <= SC_MAX_K, PC_ERR_UNSUPPORTED, "score_topk_dense: k=%d outside [1,%d]", k, SC_MAX_K);
   PC_REQUIRE(dim >= BK && dim % BK == 0 && dim <= BK * SC_MAX_KB, PC_ERR_UNSUPPORTED, "score_topk_dense: dim=%d must be a multiple of %d up to %d", dim, BK, BK * SC_MAX_KB);
   PC_REQUIRE(products > 0 && products < (int64_t(1) << 31), PC_ERR_UNSUPPORTED, "score_topk_dense: catalog size out of range");
   PC_REQUIRE(units >= 1 && units <= 4096, PC_ERR_INVALID, "score_topk_dense: bad units");
@@ -346,7 +348,7 @@ extern "C" int pc_score_topk_dense(const float* q, int64_t rows, int dim, const 
   p.tiles_per_unit = (p.n_tiles + units - 1) / units;
   p.type_id = type_id; p.row_type = row_type;
   p.part_s = reinterpret_cast<float*>(workspace);
-  p.part_i = reinterpret_cast<int32_t*>(p.part_s + size_t(rows) * units * KP);
+  p.part_i = reinterpret_cast<int32_t*>(p.part_s + size_t(rows) * units * SC_CHUNKS * KP);
   CUtensorMap map_q, map_c;
   if (int rc = make_map(&map_q, q, rows, dim, dim, BM)) return rc;
   if (int rc = make_map(&map_c, catalog, products, dim, dim, SC_BN, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return rc;
@@ -360,7 +362,7 @@ extern "C" int pc_score_topk_dense(const float* q, int64_t rows, int dim, const 
   const int grid = int(total_units < sm_count() ? total_units : sm_count());
   score_topk_tf32_kernel<<<grid, SC_THREADS, SC_SMEM, st>>>(map_q, map_c, p);
   PC_LAUNCH_CHECK();
-  rescore_topk_kernel<<<unsigned(ceil_div(rows, 8)), 256, 0, st>>>(q, catalog, dim, rows, units, p.part_s, p.part_i, k,
+  rescore_topk_kernel<<<unsigned(ceil_div(rows, 8)), 256, 0, st>>>(q, catalog, dim, rows, units * SC_CHUNKS, p.part_s, p.part_i, k,
                                                                   index_base, max_norm, out_scores, out_idx, flags);
   PC_LAUNCH_CHECK();
   return PC_OK;
