@@ -15,12 +15,14 @@
 // TMEM accumulators (the cross terms would otherwise cost a truncation at the full magnitude
 // each) and are added once, rounded, in the epilogue.
 //
-// Structure (one persistent CTA per SM, 512 threads, warp-specialised):
-//   warp 0      TMA producer: A [128 x 32] and W [bn x 32] fp32 tiles, 128-byte swizzle, 3 stages
-//   warps 8-15  compute the lo tiles of the landed activation tiles (the raw tile itself is the hi operand)
-//   warp 1      one elected lane issues the tcgen05.mma triple per K step; tcgen05.commit frees stages
-//   warps 4-7   epilogue: tcgen05.ld both accumulators (double-buffered in TMEM), bias / tanh /
-//               tanh-gradient / row-select, 128-byte row segments straight to global memory
+// Structure (one persistent CTA per SM, 640 threads, warp-specialised):
+//   warp 0 / 3    TMA producers: A [128 x 32] fp32 tiles (3 stages, HBM) / pre-split W_hi | W_lo tiles (3 stages, L2)
+//   warps 8-15    compute the lo tiles of the landed activation tiles (the raw tile itself is the hi operand)
+//   warp 1        one elected lane issues two tcgen05.mma per K step (a_hi . [W_hi | W_lo] 256 wide, a_lo . W_hi);
+//                 tcgen05.commit frees stages
+//   warps 4-7, 16-19  two epilogue sets (alternate 32-column chunks): tcgen05.ld both accumulators (double-buffered
+//                 in TMEM), bias / tanh / tanh-gradient / add / row-select - the aux operand of the gradient
+//                 epilogues arrives by TMA in the set's staging tile -, swizzled staging tile, TMA store
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -34,15 +36,17 @@ namespace {
 constexpr int MAX_BN = 128;             // columns per tile: 2 accumulators x 2 buffers x 128 = the 512 TMEM columns
 constexpr int A_BYTES = BM * BK * 4;    // 16 KB
 constexpr int B_BYTES = MAX_BN * BK * 4;  // 16 KB
-constexpr int A_STAGES = 4;             // activation tiles come from HBM: deep ring (the raw tile is the hi operand)
+constexpr int A_STAGES = 3;             // activation tiles come from HBM (the raw tile is the hi operand); the fourth
+                                        // stage was traded for a second output staging tile (two epilogue warp sets)
 constexpr int LO_STAGES = 2;            // lo tiles of A live only between the split and the MMA
 constexpr int B_STAGES = 3;             // weight tiles (pre-split hi | lo) come from L2
 constexpr int OFF_LO = A_STAGES * A_BYTES;
 constexpr int OFF_B = OFF_LO + LO_STAGES * A_BYTES;
-constexpr int OFF_OUT = OFF_B + B_STAGES * 2 * B_BYTES;   // [128 rows x 32 cols] output staging tile for the TMA store
+constexpr int OFF_OUT = OFF_B + B_STAGES * 2 * B_BYTES;   // two [128 rows x 32 cols] output staging tiles for the TMA stores
 constexpr int OUT_BYTES = BM * 32 * 4;
-constexpr int OPERAND_BYTES = OFF_OUT + OUT_BYTES;        // 64 + 32 + 96 + 16 = 208 KB
+constexpr int OPERAND_BYTES = OFF_OUT + 2 * OUT_BYTES;    // 48 + 32 + 96 + 32 = 208 KB
 constexpr int GEMM_THREADS = 512;
+constexpr int LIN_THREADS = 640;        // linear kernel: + warps 16-19 = second epilogue set
 constexpr int SPLIT_THREADS = 256;      // warps 8-15
 constexpr int SMEM_MISC = 4096;         // barriers, tmem pointer, bias
 constexpr int GEMM_SMEM = OPERAND_BYTES + 1024 + SMEM_MISC;
@@ -73,23 +77,24 @@ __global__ void split_tf32_kernel(const float4* __restrict__ w, int64_t n4, floa
   lo[i] = l;
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(LIN_THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
                      const __grid_constant__ CUtensorMap map_wlo,
                      const __grid_constant__ CUtensorMap map_out0,
-                     const __grid_constant__ CUtensorMap map_out1, const LinearParams p) {
+                     const __grid_constant__ CUtensorMap map_out1, const __grid_constant__ CUtensorMap map_aux,
+                     const LinearParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* misc = smem + OPERAND_BYTES;
   // barriers: a_full[5] a_ready[5] a_empty[5] lo_empty[2] b_full[3] b_empty[3] tmem_full[2] tmem_empty[2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
-  uint8_t* out_tile = smem + OFF_OUT;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
   float* bias_s = reinterpret_cast<float*>(misc + 512);     // up to 768 floats
   const uint32_t a_full = smem_u32(bars + 0), a_ready = smem_u32(bars + A_STAGES), a_empty = smem_u32(bars + 2 * A_STAGES);
   const uint32_t lo_empty = smem_u32(bars + 3 * A_STAGES), b_full = smem_u32(bars + 3 * A_STAGES + LO_STAGES);
   const uint32_t b_empty = smem_u32(bars + 3 * A_STAGES + LO_STAGES + B_STAGES);
   const uint32_t tfull_bar = smem_u32(bars + 3 * A_STAGES + LO_STAGES + 2 * B_STAGES), tempty_bar = tfull_bar + 16;
+  const uint32_t aux_bar = tempty_bar + 16;   // [2]: the aux chunk of an epilogue set has landed in its staging tile
   const int warp = warp_id(), lane = lane_id();
 
   if (threadIdx.x == 0) {
@@ -105,11 +110,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
-      mbar_init(tempty_bar + 8 * s, 128);
+      mbar_init(tempty_bar + 8 * s, 256);
+      mbar_init(aux_bar + 8 * s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.n; i += GEMM_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.n; i += LIN_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -207,7 +213,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         acc_phase ^= 1;
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 16) {
     // ---------------- activation split.  The raw fp32 tile IS the hi operand: under kind::tf32 the tensor core
     // ignores the low 13 mantissa bits, so hi = trunc_tf32(x) needs no rewrite; only lo = rn_tf32(x - hi) is
     // written (to the lo ring).  x = hi + (x - hi) exactly and |lo| < 2^-10 |x|.
@@ -239,16 +245,25 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
   } else if (warp >= 4) {
     // ---------------- epilogue: TMEM -> registers -> (bias / activation) -> swizzled smem tile -> TMA store
+    // two sets of four warps (4-7 and 16-19; warp % 4 = TMEM lane quarter): set s takes the 32-column chunks
+    // s, s + 2, ... of every tile and has its own staging tile and named barrier.  One warp per scheduler could not
+    // hide its own latencies in the tanh / aux epilogues (profiles/gemm_epilogue_bench.py).
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int quad = warp - 4;
+    const int set = warp >= 16 ? 1 : 0;
+    const int quad = warp & 3;
     const int trow = quad * 32 + lane;                      // row of the tile this thread owns
-    const bool issuer = threadIdx.x == 128;                 // first epilogue thread issues the bulk stores
+    const bool issuer = quad == 0 && lane == 0;             // first thread of the set issues its bulk stores
+    uint8_t* out_tile = smem + OFF_OUT + set * OUT_BYTES;
     const uint32_t bias_addr = smem_u32(bias_s), out_addr = smem_u32(out_tile);
-    // epilogues that read `aux` (one 128-byte row segment per thread and 32-column chunk) were latency-bound on those
-    // loads (0.95 vs 0.38 ms for 128 -> 256 with / without aux): the rows of the NEXT tile are pulled into L2 by one
-    // bulk prefetch per thread a whole tile ahead
-    const bool has_aux = p.epilogue == EPI_TANH_GRAD || p.epilogue == EPI_BIAS_ADD || p.epilogue == EPI_BIAS_SELECT;
+    // tanh-gradient / add epilogues read a whole [128 x 32] tile of `aux` per chunk.  As per-thread row loads that is
+    // 32 L1 wavefronts per instruction (0.95 vs 0.38 ms for 128 -> 256 with / without aux); instead the issuer TMA-loads
+    // the aux chunk into the set's staging tile (same swizzle as the output), every thread combines its own row in
+    // place and the tile goes out again as the result.  The rows of the NEXT tile are pulled into L2 a tile ahead.
+    // The row-select epilogue only needs aux for rows without neighbours and keeps plain loads.
+    const bool aux_tile = p.epilogue == EPI_TANH_GRAD || p.epilogue == EPI_BIAS_ADD;
+    const bool has_aux = aux_tile || p.epilogue == EPI_BIAS_SELECT;
+    uint32_t aux_phase = 0;
     auto prefetch_aux = [&](int64_t tile) {
       if (!has_aux || tile >= tiles) return;
       const int64_t prow = (tile / p.n_tiles) * BM + trow;
@@ -267,7 +282,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tc_fence_after();
       bool keep = true;
       if (p.epilogue == EPI_BIAS_SELECT && row < p.m) keep = p.rowptr[row + 1] > p.rowptr[row];
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      for (int c0 = set * 32; c0 < p.bn; c0 += 64) {
+        if (aux_tile && issuer) {   // the staging tile is free once the previous store has read it
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive_expect_tx(aux_bar + 8 * set, OUT_BYTES);
+          tma_load_2d(out_addr, &map_aux, n0 + c0, m0, aux_bar + 8 * set);
+        }
         uint32_t r[32], rc[32];
         tmem_ld32_async(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + c0), r);
         tmem_ld32_async(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 2 * MAX_BN + MAX_BN + c0), rc);
@@ -286,28 +306,36 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (p.epilogue == EPI_BIAS_TANH) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = tanhf(y[j]);
-        } else if (p.epilogue != EPI_BIAS && row < p.m) {
+        } else if (aux_tile) {
+          mbar_wait(aux_bar + 8 * set, aux_phase);   // implies the issuer saw the previous store finish reading the tile
+          aux_phase ^= 1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {              // my own row of the aux chunk, same swizzle as the output below
+            const float4 a = lds128(out_addr + trow * 128 + ((j ^ (trow & 7)) << 4));
+            if (p.epilogue == EPI_TANH_GRAD) {
+              y[4 * j] *= 1.f - a.x * a.x; y[4 * j + 1] *= 1.f - a.y * a.y; y[4 * j + 2] *= 1.f - a.z * a.z; y[4 * j + 3] *= 1.f - a.w * a.w;
+            } else {
+              y[4 * j] += a.x; y[4 * j + 1] += a.y; y[4 * j + 2] += a.z; y[4 * j + 3] += a.w;
+            }
+          }
+        } else if (p.epilogue == EPI_BIAS_SELECT && !keep && row < p.m) {
           const float* aux = p.aux + row * p.ld_aux + n;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 a = *reinterpret_cast<const float4*>(aux + j);
-            if (p.epilogue == EPI_TANH_GRAD) {
-              y[j] *= 1.f - a.x * a.x; y[j + 1] *= 1.f - a.y * a.y; y[j + 2] *= 1.f - a.z * a.z; y[j + 3] *= 1.f - a.w * a.w;
-            } else if (p.epilogue == EPI_BIAS_ADD) {
-              y[j] += a.x; y[j + 1] += a.y; y[j + 2] += a.z; y[j + 3] += a.w;
-            } else if (!keep) {  // EPI_BIAS_SELECT
-              y[j] = a.x; y[j + 1] = a.y; y[j + 2] = a.z; y[j + 3] = a.w;
-            }
+            y[j] = a.x; y[j + 1] = a.y; y[j + 2] = a.z; y[j + 3] = a.w;
           }
         }
-        // the previous chunk's bulk store must have finished reading the staging tile
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!aux_tile) {
+          // the previous chunk's bulk store must have finished reading the staging tile
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)   // 128-byte swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
           sts128(out_addr + trow * 128 + ((j ^ (trow & 7)) << 4), make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]));
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
         if (issuer) {
           const bool first = n < p.split;
           const CUtensorMap* map = first ? &map_out0 : &map_out1;
@@ -625,6 +653,11 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   } else {
     map_out1 = map_out0;
   }
+  CUtensorMap map_aux = map_out0;
+  if (epilogue == EPI_TANH_GRAD || epilogue == EPI_BIAS_ADD) {
+    PC_REQUIRE(reinterpret_cast<uintptr_t>(aux) % 16 == 0, PC_ERR_INVALID, "linear: aux must be 16-byte aligned (TMA)");
+    if (int rc = make_map(&map_aux, aux, m, n, ld_aux, BM)) return rc;
+  }
   static bool configured = false;
   if (!configured) {
     PC_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
@@ -632,7 +665,7 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   }
   const int64_t tiles = ((m + BM - 1) / BM) * p.n_tiles;
   const int grid = int(tiles < sm_count() ? tiles : sm_count());
-  linear_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out0, map_out1, p);
+  linear_tf32x3_kernel<<<grid, LIN_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out0, map_out1, map_aux, p);
   PC_LAUNCH_CHECK();
   return PC_OK;
 }
