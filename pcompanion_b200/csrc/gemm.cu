@@ -383,7 +383,8 @@ constexpr int WG_DY_BYTES = BM * WG_ROWS * 4;      // 8 KB: 128 columns x 16 row
 constexpr int WG_X_BYTES = WG_MAX_K * WG_ROWS * 4; // 16 KB
 constexpr int WG_OFF_X = 2 * WG_DY_BYTES;          // raw X starts here; its lo tile follows at + k * WG_ROWS * 4
 constexpr int WG_STAGE_BYTES = 2 * (WG_DY_BYTES + WG_X_BYTES);     // 48 KB
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + SMEM_MISC;   // 192 KB + misc
+constexpr int WG_OUT_BYTES = BM * 32 * 4;            // [128 x 32] staging tile of the flush (TMA store / reduce-add)
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + WG_OUT_BYTES + 1024 + SMEM_MISC;   // 192 + 16 KB + misc
 constexpr int WG_GROUP_BYTES = WG_ROWS * 128;      // one 32-column group of a stage
 constexpr int WG_FLUSH = 32;                       // blocks per accumulation chain
 
@@ -415,10 +416,11 @@ using WgPipe = Ring<WG_STAGES>;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
-                    const WgradParams p) {
+                    const __grid_constant__ CUtensorMap map_pw, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* misc = smem + WG_STAGES * WG_STAGE_BYTES;
+  uint8_t* wg_out = smem + WG_STAGES * WG_STAGE_BYTES;
+  uint8_t* misc = wg_out + WG_OUT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // full[S], ready[S], empty[S], lo_empty[L], tmem_full, tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
   const uint32_t full_bar = smem_u32(bars + 0), ready_bar = smem_u32(bars + WG_STAGES), empty_bar = smem_u32(bars + 2 * WG_STAGES);
@@ -552,31 +554,50 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
     if (chains == 0) {
       for (int c0 = 0; c0 < p.k; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // A chain's [128 x k] result leaves through a swizzled staging tile and TMA: a plain store for the first chain,
+    // a reduce-add (cp.reduce.async.bulk.tensor .add) into the CTA's partial for the following ones.  (As per-thread
+    // row read-modify-writes every load / store instruction touched 32 different rows.)  One chain's operations are
+    // complete before the next chain's are issued, so the additions happen in chain order: deterministic.
+    const int trow = quad * 32 + lane;
+    const bool issuer = threadIdx.x == 128;
+    const uint32_t out_addr = smem_u32(wg_out);
+    const int prow0 = subset * p.n + half * BM;               // first row of this CTA's tile in the [subsets * n, k] partials
     for (int64_t ch = 0; ch < chains; ++ch) {
       mbar_wait(tfull_bar, phase);
       tc_fence_after();
+      if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // previous chain fully applied
       for (int c0 = 0; c0 < p.k; c0 += 32) {
         uint32_t r[32], rc[32];
         tmem_ld32_async(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
         tmem_ld32_async(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(p.k + c0), rc);
         tmem_ld_wait32(r);
         tmem_ld_wait32(rc);
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
+        asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v = make_float4(__uint_as_float(r[j]) + __uint_as_float(rc[j]), __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]),
-                                 __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]), __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]));
-          float4* dst = reinterpret_cast<float4*>(out + c0 + j);
-          if (ch > 0) {
-            const float4 o = *dst;
-            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-          }
-          *dst = v;
+        for (int j = 0; j < 8; ++j)   // 128-byte swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+          sts128(out_addr + trow * 128 + ((j ^ (trow & 7)) << 4),
+                 make_float4(__uint_as_float(r[4 * j]) + __uint_as_float(rc[4 * j]), __uint_as_float(r[4 * j + 1]) + __uint_as_float(rc[4 * j + 1]),
+                             __uint_as_float(r[4 * j + 2]) + __uint_as_float(rc[4 * j + 2]), __uint_as_float(r[4 * j + 3]) + __uint_as_float(rc[4 * j + 3])));
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          if (ch == 0)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&map_pw), "r"(c0),
+                         "r"(prow0), "r"(out_addr)
+                         : "memory");
+          else
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&map_pw),
+                         "r"(c0), "r"(prow0), "r"(out_addr)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar);
       phase ^= 1;
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -707,16 +728,17 @@ extern "C" int pc_wgrad_tf32x3(const float* dy, int64_t m, int n, int64_t ld_dy,
   p.m = m; p.n = n; p.k = k; p.halves = halves;
   p.partial_w = reinterpret_cast<float*>(workspace);
   p.partial_b = db ? p.partial_w + size_t(subsets) * n * k : nullptr;
-  CUtensorMap map_dy, map_x;
+  CUtensorMap map_dy, map_x, map_pw;
   if (int rc = make_map_mn(&map_dy, dy, m, n, ld_dy, 4)) return rc;
   if (int rc = make_map_mn(&map_x, x, m, k, ld_x, k / 32)) return rc;
+  if (int rc = make_map(&map_pw, p.partial_w, int64_t(subsets) * n, k, k, BM)) return rc;
   static bool configured = false;
   if (!configured) {
     PC_CUDA(cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     configured = true;
   }
   cudaStream_t st = as_stream(stream);
-  wgrad_tf32x3_kernel<<<grid, GEMM_THREADS, WG_SMEM, st>>>(map_dy, map_x, p);
+  wgrad_tf32x3_kernel<<<grid, GEMM_THREADS, WG_SMEM, st>>>(map_dy, map_x, map_pw, p);
   PC_LAUNCH_CHECK();
   const int64_t nk = int64_t(n) * k;
   reduce_partials_kernel<<<unsigned((nk + 255) / 256), 256, 0, st>>>(p.partial_w, subsets, nk, dw);
