@@ -47,40 +47,50 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  The process is started BEFORE the warm-up (its start-up
+    takes driver locks that stall kernel launches for tens of ms - enough to halve a 40 ms timed region); `mark()` is
+    called when the timed region starts and only samples taken after it are reported (all of them if the region was
+    shorter than one sampling period)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.proc = None
+        self.t_mark = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
+
+    def mark(self):
+        self.t_mark = time.time()
+        return self
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        import datetime
+        time.sleep(0.15)
         self.proc.terminate()
         out = self.proc.communicate()[0]
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if self.t_mark is None or r[0] >= self.t_mark - 0.05]
+        use = inside if inside else rows[-1:]
+        sm = sorted(r[1] for r in use)
+        reasons = sorted({n for r in use for n in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in use), default=None),
+                "samples": len(use), "reasons": reasons}
 
 
 def make_cfg(device):
@@ -161,12 +171,13 @@ def run_ours(args):
             loss = step(xs, ts)
             loss_host.copy_(loss.detach(), non_blocking=True)
 
+    sampler = ClockSampler(local)
     for _ in range(args.warmup):
         step(x_dev, trip)
     torch.cuda.synchronize()
 
     # ---- device-resident timed region (per-kernel events on the launching stream)
-    sampler = ClockSampler(local)
+    sampler.mark()
     _lib.PROFILE = []
     launches0 = _lib.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -293,9 +304,11 @@ def run_pcompanion(args, rank, world, dev):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    sampler = ClockSampler(dev.index)
     for _ in range(args.warmup):
         step(batch)
-    sampler = ClockSampler(dev.index)
+    torch.cuda.synchronize()
+    sampler.mark()
     l0 = _lib.LAUNCHES
     ms = timed(lambda: step(batch), args.steps)
     launches = _lib.LAUNCHES - l0
@@ -350,12 +363,17 @@ def run_retrieval(args, rank, world, dev):
         assert world == 1, "--dense is a single-GPU measurement"
     else:
         topk = cat.topk
-    for _ in range(args.warmup):
+    # a step is only a few ms: warm up for at least W steps AND ~0.5 s, so that the timed region does not start on a GPU
+    # that is still ramping its clocks after the host-side setup
+    sampler = ClockSampler(dev.index)
+    t_warm, n_warm = time.perf_counter(), 0
+    while n_warm < args.warmup or time.perf_counter() - t_warm < 0.5:
         topk(queries, k, row_type)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        n_warm += 1
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(dev.index)
+    sampler.mark()
     launches0 = _lib.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

@@ -394,9 +394,11 @@ def run_partitioned_bench(args, rank: int, world: int, dev: torch.device) -> Non
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), out
 
+    sampler = B.ClockSampler(dev.index)
     for _ in range(args.warmup):
         step(x, trip)
-    sampler = B.ClockSampler(dev.index)
+    torch.cuda.synchronize()
+    sampler.mark()
     launches0 = _lib.LAUNCHES
     ms, loss = timed(lambda: step(x, trip), args.steps)
     launches = _lib.LAUNCHES - launches0
