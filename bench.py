@@ -405,7 +405,7 @@ def run_retrieval(args, rank, world, dev):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"C4: top-10 over 10M-product catalog, 1K types, {q_n} queries x 3 type rows, "
-                                       f"catalog sharded over {world} GPU(s), " + ("dense tcgen05 3xTF32 scoring GEMM + per-type mask + "
+                                       f"catalog sharded over {world} GPU(s), " + ("dense tcgen05 TF32 scoring GEMM + per-type mask + "
                                        "fused candidate top-K + exact fp64 re-scoring" if args.dense else "type-segmented exact fp64 scoring")},
                 "roofline": {"bound": "hbm", "achieved": bytes_read / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": bytes_read / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,

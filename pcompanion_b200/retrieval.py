@@ -111,7 +111,7 @@ class CatalogIndex:
         return ops.topk_segments(queries, self.catalog, beg, end, k, self.members, self.index_base, splits)
 
     def topk_dense(self, queries: torch.Tensor, k: int, row_type: Optional[torch.Tensor] = None):
-        """Same result as ``topk`` through the dense tensor-core path (BASELINE north_star part 4): 3xTF32 scoring
+        """Same result as ``topk`` through the dense tensor-core path (BASELINE north_star part 4): single-pass TF32 scoring
         GEMM over the whole catalog, per-type mask and candidate selection in the epilogue, exact fp64 re-scoring.
         Rows whose guard band fails are re-run on the exact segmented kernel, so the output is always exact."""
         queries = queries.contiguous().float()
