@@ -123,6 +123,27 @@ class HaloPlan:
         return self.n_halo * width * 4
 
 
+def peer_layout(c: List[List[int]], n_loc: List[int], rank: int) -> dict:
+    """Where halo rows live in the peers' buffers.  c[q][p] = rows rank q receives from rank p, n_loc[q] = rows q owns.
+    forward: my send list is grouped by destination peer p; in p's [local | halo] table my rows follow p's own rows and
+    the rows of the ranks before me.  reverse: my halo partials are grouped by owner p; in p's return buffer (grouped
+    by the rank that holds the partials) my run follows the runs of the ranks before me."""
+    world = len(n_loc)
+    f_off, r_off = [0], [0]
+    for p in range(world):
+        f_off.append(f_off[-1] + c[p][rank])                       # rows I send to p = rows p receives from me
+        r_off.append(r_off[-1] + c[rank][p])
+    return {
+        "table_rows": max(n_loc[q] + sum(c[q]) for q in range(world)),
+        "return_rows": max(1, max(sum(c[q][p] for q in range(world)) for p in range(world))),
+        "f_off": f_off,
+        "f_dst": [n_loc[p] + sum(c[p][:rank]) for p in range(world)],
+        "r_src": [n_loc[rank] + r_off[p] for p in range(world)],
+        "r_cnt": [c[rank][p] for p in range(world)],
+        "r_dst": [sum(c[q][p] for q in range(rank)) for p in range(world)],
+    }
+
+
 class PeerHalo:
     """Halo rows moved by our own kernel over NVLink / NVSwitch peer memory instead of a NCCL all-to-all.
 
@@ -146,8 +167,8 @@ class PeerHalo:
         dist.all_gather_into_tensor(allc, mine, group=group)
         c = allc.tolist()                                             # c[q][p] = rows rank q receives from rank p
         n_loc = [plan.bounds[q + 1] - plan.bounds[q] for q in range(world)]
-        self.table_rows = max(n_loc[q] + sum(c[q]) for q in range(world))
-        self.return_rows = max(1, max(sum(c[q][p] for q in range(world)) for p in range(world)))
+        lay = peer_layout(c, n_loc, rank)
+        self.table_rows, self.return_rows = lay["table_rows"], lay["return_rows"]
         self._kv = symm.empty(self.table_rows * width, dtype=torch.float32, device=dev)
         self._ret = symm.empty(self.return_rows * width, dtype=torch.float32, device=dev)
         h_kv = symm.rendezvous(self._kv, group.group_name)
@@ -155,25 +176,15 @@ class PeerHalo:
         self._handles = (h_kv, h_ret)
         i64, fp = ctypes.c_int64 * (world + 1), ctypes.c_void_p * world
         i64w = ctypes.c_int64 * world
-        # forward: my send list is grouped by destination peer p; in p's table my rows follow p's own rows and the
-        # rows of the ranks before me
-        off = [0]
-        for p in range(world):
-            off.append(off[-1] + plan.send_counts[p])
-        self._f_off = i64(*off)
-        self._f_first = off[(rank + 1) % world]                       # staggered start: rank r begins with peer r+1
+        self._f_off = i64(*lay["f_off"])
+        self._f_first = lay["f_off"][(rank + 1) % world]              # staggered start: rank r begins with peer r+1
         self._f_base = fp(*[int(h_kv.buffer_ptrs[p]) if plan.send_counts[p] else None for p in range(world)])
-        self._f_dst = i64w(*[n_loc[p] + sum(c[p][:rank]) for p in range(world)])
-        # reverse: my halo partials are grouped by owner p; in p's return buffer (grouped by the rank that holds the
-        # partials) my run follows the runs of the ranks before me
-        roff = [0]
-        for p in range(world):
-            roff.append(roff[-1] + c[rank][p])
+        self._f_dst = i64w(*lay["f_dst"])
         self._r_copy = []
         for p in range(world):
-            cnt, dst0 = c[rank][p], sum(c[q][p] for q in range(rank))
+            cnt, dst0 = lay["r_cnt"][p], lay["r_dst"][p]
             view = h_ret.get_buffer(p, (self.return_rows, width), torch.float32)[dst0: dst0 + cnt] if cnt else None
-            self._r_copy.append((n_loc[rank] + roff[p], cnt, view))
+            self._r_copy.append((lay["r_src"][p], cnt, view))
         self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
         self._group = group
         self.version = 0

@@ -114,3 +114,73 @@ def test_halo_plan_single_rank_is_identity():
     plan = HaloPlan(torch.tensor(rowptr), torch.tensor(col), [0, n], 0)
     assert plan.n_halo == 0 and plan.send_idx.numel() == 0
     assert np.array_equal(plan.col_ext.numpy(), col.astype(np.int64))
+
+
+def _layout_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pcompanion_b200.distributed import HaloPlan, peer_layout
+        n, rowptr, col, q, kv, d_o = _global_problem()
+        bounds = [0, 9, 30, 31, n]                                   # uneven partition, one rank owns a single row
+        b0, b1 = bounds[rank], bounds[rank + 1]
+        lp = rowptr[b0:b1 + 1] - rowptr[b0]
+        lcol = col[rowptr[b0]:rowptr[b1]]
+        plan = HaloPlan(torch.tensor(lp), torch.tensor(lcol), bounds, rank)
+        counts = [None] * world
+        dist.all_gather_object(counts, plan.recv_counts)             # c[q][p] = rows q receives from p
+        n_loc = [bounds[i + 1] - bounds[i] for i in range(world)]
+        lay = peer_layout(counts, n_loc, rank)
+        assert lay["f_off"] == [sum(plan.send_counts[:p]) for p in range(world + 1)]
+        # simulate the peer-memory transport: every rank publishes what it would store where, then applies the
+        # stores addressed to it and compares with the all-to-all transport
+        kv_loc = torch.tensor(kv[b0:b1])
+        pushes = [(p, lay["f_dst"][p], kv_loc[plan.send_idx[lay["f_off"][p]: lay["f_off"][p + 1]]].numpy()) for p in range(world)]
+        everyone = [None] * world
+        dist.all_gather_object(everyone, pushes)
+        table = np.full((lay["table_rows"], kv.shape[1]), np.nan)
+        table[: plan.n_local] = kv[b0:b1]
+        for src_pushes in everyone:
+            for dst_rank, row0, rows in src_pushes:
+                if dst_rank == rank and len(rows):
+                    assert np.isnan(table[row0: row0 + len(rows)]).all()          # no two peers write the same rows
+                    table[row0: row0 + len(rows)] = rows
+        recv = torch.empty(plan.n_halo, kv.shape[1], dtype=kv_loc.dtype)
+        plan.forward_exchange(kv_loc[plan.send_idx].contiguous(), recv)
+        assert np.array_equal(table[plan.n_local: plan.n_local + plan.n_halo], recv.numpy())
+        # reverse direction: runs of halo partials land in the owners' return buffers exactly where the all-to-all puts them
+        part = np.arange(plan.n_halo * 3, dtype=np.float64).reshape(plan.n_halo, 3) + 1000 * rank
+        ext = np.concatenate([np.zeros((plan.n_local, 3)), part])
+        rpush = [(p, lay["r_dst"][p], ext[lay["r_src"][p]: lay["r_src"][p] + lay["r_cnt"][p]]) for p in range(world)]
+        dist.all_gather_object(everyone, rpush)
+        ret = np.full((lay["return_rows"], 3), np.nan)
+        for src_pushes in everyone:
+            for dst_rank, row0, rows in src_pushes:
+                if dst_rank == rank and len(rows):
+                    assert np.isnan(ret[row0: row0 + len(rows)]).all()
+                    ret[row0: row0 + len(rows)] = rows
+        returned = torch.empty(plan.send_idx.numel(), 3, dtype=torch.float64)
+        plan.reverse_exchange(torch.tensor(part), returned)
+        assert np.array_equal(ret[: plan.send_idx.numel()], returned.numpy())
+        # slot table of the one-pass owner-side reduction
+        off = 0
+        for p, cnt in enumerate(plan.send_counts):
+            ids = plan.send_idx[off: off + cnt]
+            assert torch.equal(plan.slot[p, ids].long(), torch.arange(off, off + cnt))
+            assert int((plan.slot[p] >= 0).sum()) == cnt
+            off += cnt
+        results[rank] = "ok"
+    except Exception:  # pragma: no cover
+        import traceback
+        results[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_layout_matches_all_to_all_world4():
+    """The offsets PeerHalo hands to pc_halo_push / the copy engines (peer_layout), simulated on 4 CPU ranks: every
+    store lands exactly where the NCCL all-to-all transport would have put the row, in both directions."""
+    world = 4
+    results = mp.Manager().dict()
+    mp.spawn(_layout_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert all(results.get(r) == "ok" for r in range(world)), dict(results)
