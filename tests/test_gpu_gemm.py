@@ -151,3 +151,27 @@ def test_norm_kernels_match_float64():
     kept, rest = ops.mask_split(g128, rowptr)
     has = (torch.arange(m, device=dev()) % 4 != 0).unsqueeze(1)
     assert torch.equal(kept, torch.where(has, g128, torch.zeros_like(g128))) and torch.equal(kept + rest, g128)
+
+
+def test_type_scores_tensor_core_path_matches_float64():
+    """P-Companion's [B, L] x [L, T] type scoring on the tcgen05 kernel (large batches: 768-column chunks into the strided
+    [B, T] output, library GEMM for the last T % 32 columns) and its dense autograd fallback."""
+    from pcompanion_b200.dense import type_scores, _TypeScoresTC
+    g = torch.Generator(device=dev()).manual_seed(11)
+    b, l, t = 16_384, 64, 34_800                                       # reference defaults: TYPE_EMB_DIM 64, NUM_TYPES 34,800
+    base = torch.randn(b, l, generator=g, device=dev(), requires_grad=True)
+    w = (torch.randn(t, l, generator=g, device=dev()) * 0.1).requires_grad_(True)
+    s = type_scores(base, w)
+    assert s.shape == (b, t) and isinstance(s.grad_fn, _TypeScoresTC._backward_cls)
+    rows = torch.tensor([0, 1, 4097, b - 1], device=dev())
+    close(s[rows], (base[rows].double() @ w.double().t()).detach().cpu().numpy(), what="type scores")
+    cols = torch.tensor([0, 767, 768, 34_783, 34_784, t - 1], device=dev())   # chunk borders and the library-GEMM tail
+    close(s[:, cols], (base.double() @ w[cols].double().t()).detach().cpu().numpy(), what="type score columns")
+    small = type_scores(base[:256], w)                                 # below the launch-count threshold: one library GEMM
+    close(small, (base[:256].double() @ w.double().t()).detach().cpu().numpy(), what="type scores (small batch)")
+    d = torch.zeros_like(s)
+    d[rows[:, None], cols[None, :]] = 1.0
+    s.backward(d)
+    ref_db = d.double() @ w.double()
+    close(base.grad, ref_db.detach().cpu().numpy(), what="d base", atol=1e-9)
+    close(w.grad[cols], (d.double().t() @ base.double())[cols].detach().cpu().numpy(), what="d weight")
