@@ -1,17 +1,27 @@
 #!/usr/bin/env python
-"""Benchmark of the P-Companion hot path on B200 (contract: see the task statement / DESIGN.md).
+"""Benchmark of the P-Companion hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload gat|retrieval|pcompanion]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload all|gat|retrieval|retrieval_dense|pcompanion|c1|c5]
 
-Default workload = BASELINE.json configs[1]: synthetic BPG with 1 M products / ~20 M co-view
-edges per GPU, one step = full-graph Product2Vec GAT forward + triplet hinge + backward + Adam
-(every destination, every edge, per-node FFN / QKV / out-proj included).  Metric: co-view edges
-processed per second, whole job.  Prints ONE JSON line on rank 0.
+BASELINE.json's metric has two halves - "GAT edges/sec fwd+bwd (Product2Vec) & top-K queries/sec at 1/2/4/8 B200" -
+so the default run (`--workload all`) measures both and prints ONE JSON line on rank 0:
+
+* the line itself is configs[1] (C2): synthetic BPG with 1 M products / ~20 M co-view edges per GPU, one step = full-graph
+  Product2Vec GAT forward + triplet hinge + backward + Adam (every destination, every edge, per-node FFN / QKV /
+  out-proj included); `value` = co-view edges per second, whole job; at N > 1 the graph is node-partitioned with a halo
+  exchange and the line carries the multi-GPU parity check that ran before the timing;
+* `retrieval` (C4: masked top-10 over a 10 M-product catalog, 1 K types, sharded over the ranks) and, at N = 1,
+  `retrieval_dense` (the north-star's tensor-core wording of the same query) - `topk_queries_per_sec` repeats the value;
+* `pcompanion` (C3: joint P-Companion step on a 1 M-product table, 34,800 types, batch 256 and 65,536).
+
+Every sub-record has its own value / ms_per_step / roofline / e2e (/ cpu_baseline at N = 1).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -28,6 +38,7 @@ EDGES_PER_GPU = 20_000_000
 TRIPLETS = 131_072
 KNEG = 5
 SEED = 1234
+FP64_TFLOPS_NOMINAL = 37.0   # B200 vector fp64 (HGX B200: 296 TFLOP/s per 8 GPUs); no measured figure in MEASURED_PEAKS.json
 
 # algorithmic bytes of the three sparse kernels (fp32, per edge / per node)
 ALGO_BYTES = {
@@ -44,6 +55,15 @@ def measured_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops_sustained"]), "measured bf16 sustained (MEASURED_PEAKS.json); kind::tf32 runs at half the bf16 rate"
+    return 1400.0, "fallback (B200_PROFILING.md); kind::tf32 runs at half the bf16 rate"
 
 
 class ClockSampler:
@@ -99,28 +119,62 @@ def make_cfg(device):
                            MARGIN=1.0, ALPHA=0.8, NUM_COMP_TYPES=3, NUM_TYPES=34800, LEARNING_RATE=1e-3, DEVICE=device)
 
 
-# ----------------------------------------------------------------------------- our arm
-def run_ours(args):
+def _dist():
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    return dist
+
+
+def max_over_ranks(values, dev, world):
+    t = torch.tensor(list(values), dtype=torch.float64, device=dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        _dist().all_reduce(t, op=_dist().ReduceOp.MAX)
+    return t.tolist()
+
+
+class L2Flush:
+    """Between timed iterations of a leg whose working set fits the 126 MB L2: overwrite a 256 MB buffer (not timed)."""
+
+    def __init__(self, dev):
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def timed_steps(fn, steps, dev, world, flush=None):
+    """Average device time of `steps` calls of fn (CUDA events on the current stream, barrier + synchronize on both sides,
+    max over ranks).  With `flush` every step is timed on its own and the L2 flush between the steps is not."""
+    torch.cuda.synchronize()
+    if world > 1:
+        _dist().barrier()
+    out = None
+    if flush is None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            out = fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / steps
+    else:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush()
+            a.record()
+            out = fn()
+            b.record()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    if world > 1:
+        _dist().barrier()
+    return max_over_ranks([ms], dev, world)[0], out
+
+
+# ============================================================================= GAT leg, one GPU (C2)
+def gat_single(args, dev):
     import pcompanion_b200 as pc
-    from pcompanion_b200 import _lib, ops
+    from pcompanion_b200 import _lib
     from pcompanion_b200.synthetic import synthetic_bpg
-
-    if args.workload == "retrieval":
-        return run_retrieval(args, rank, world, dev)
-    if args.workload == "pcompanion":
-        return run_pcompanion(args, rank, world, dev)
-    if world > 1:
-        from pcompanion_b200.distributed import run_partitioned_bench
-        return run_partitioned_bench(args, rank, world, dev)
-
     torch.manual_seed(SEED)
     t0 = time.perf_counter()
     bpg = synthetic_bpg(NODES_PER_GPU, EDGES_PER_GPU, seed=SEED, device=dev)
@@ -171,7 +225,7 @@ def run_ours(args):
             loss = step(xs, ts)
             loss_host.copy_(loss.detach(), non_blocking=True)
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     for _ in range(args.warmup):
         step(x_dev, trip)
     torch.cuda.synchronize()
@@ -208,18 +262,24 @@ def run_ours(args):
     sparse_ms = sum(k["ms"] for k in kernels.values())
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_gat_dram_traffic.json")
-    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        with open(tpath) as f:
-            tj = json.load(f)
-        if dom in tj["kernels"]:
-            traffic, traffic_src = tj["kernels"][dom]["dram_bytes"], "profiles/r1_gat_dram_traffic.json (ncu --set full, same workload)"
+    for tname in ("r2_gat_dram_traffic.json", "r1_gat_dram_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            with open(tpath) as f:
+                tj = json.load(f)
+            if dom in tj["kernels"]:
+                traffic, traffic_src = tj["kernels"][dom]["dram_bytes"], f"profiles/{tname} (ncu --set full, same workload)"
+                break
+    whole = (3152 * e + 3676 * n) / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algo_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES[dom][0] * e + ALGO_BYTES[dom][1] * n, "peak_source": peak_src,
                 "sparse_fwd_bwd": {"ms": round(sparse_ms, 4),
                                    "algo_gbs": round((3152 * e + 3676 * n) / (sparse_ms * 1e-3) / 1e9, 1),
                                    "frac": round((3152 * e + 3676 * n) / (sparse_ms * 1e-3) / 1e9 / peak, 4)},
+                "whole_step": {"ms": round(ms_per_step, 4), "algo_gbs": round(whole, 1), "frac": round(whole / peak, 4),
+                               "note": "SURVEY 8(d) unit: the sparse kernels' algorithmic bytes against the WHOLE step "
+                                       "(projections, BatchNorm, loss and Adam included)"},
                 "kernels": kernels,
                 "abi_ms_per_step": abi_ms, "abi_calls_per_step": abi_calls,
                 "abi_total_ms_per_step": round(sum(abi_ms.values()), 3)}
@@ -234,8 +294,8 @@ def run_ours(args):
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
 
     csr_build = time_csr_build(graph, peak)
-    cpu = None if args.skip_cpu else cpu_baseline_gat(bpg, graph, cfg, seconds=15.0)
-    line = {
+    cpu = None if args.skip_cpu else cpu_baseline_gat(bpg, graph, cfg, seconds=12.0)
+    return {
         "metric": "gat_edges_per_sec_fwd_bwd", "value": e / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -250,18 +310,168 @@ def run_ours(args):
                 "h2d_bytes_per_step": x_host.numel() * 4 + trip_host.numel() * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "loss": float(loss.item()),
     }
-    print(json.dumps(line))
 
 
-def run_pcompanion(args, rank, world, dev):
+# ============================================================================= GAT leg, node-partitioned (N > 1)
+def gat_partitioned(args, rank, world, dev, nodes_per_gpu=NODES_PER_GPU, edges_per_gpu=EDGES_PER_GPU, label="C5-style weak scaling"):
+    """Node-partitioned Product2Vec step: `nodes_per_gpu` products / ~`edges_per_gpu` co-view edges per GPU, columns uniform over
+    the global node range, so (N-1)/N of every rank's edges point at halo rows.  Runs the multi-GPU parity check first."""
+    dist = _dist()
+    import pcompanion_b200 as pc
+    from pcompanion_b200 import _lib
+    from pcompanion_b200.distributed import (HaloPlan, allreduce_gradients, forward_graph_partitioned, halo_gather,
+                                              partition_edges)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _partition_check import check_partitioned
+    parity = check_partitioned(rank, world, dev)        # also warms NCCL (communicator, all-to-all, symmetric memory)
+    if not parity["ok"]:
+        if rank == 0:
+            print(json.dumps({"metric": "gat_edges_per_sec_fwd_bwd", "error": "multi-GPU parity check failed", "parity": parity}))
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(3)
+    n_loc, e_loc = nodes_per_gpu, edges_per_gpu
+    n_total = n_loc * world
+    bounds = [i * n_loc for i in range(world + 1)]
+    g = torch.Generator(device=dev).manual_seed(SEED + 100 + rank)
+    # every rank draws its share of the GLOBAL edge list; the owners of the rows get them through the distributed
+    # CSR build (one all-to-all of keys, then local sort / unique) - timed separately, outside the step
+    rows = torch.randint(0, n_total, (e_loc,), generator=g, device=dev, dtype=torch.int32)
+    cols = torch.randint(0, n_total, (e_loc,), generator=g, device=dev, dtype=torch.int32)
+    partition_edges(rows[:4096], cols[:4096], bounds, rank)             # untimed warm-up of the exchange
+    torch.cuda.synchronize(); dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    rowptr, col_global = partition_edges(rows, cols, bounds, rank)
+    ev1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    build_ms = max_over_ranks([ev0.elapsed_time(ev1)], dev, world)[0]
+    del rows, cols
+    plan = HaloPlan(rowptr, col_global, bounds, rank)
+    plan.graph.transposed()
+    peer_ok = plan.enable_peer_memory()
+    transport = ("pc_halo_push: gather + NVLink stores into the peers' symmetric-memory tables, one launch per direction"
+                 if peer_ok else "NCCL all_to_all_single (" + getattr(plan, "peer_error", "peer memory disabled") + ")")
+    e_local = col_global.numel()
+    x = torch.randn(n_loc, 128, generator=g, device=dev)
+    cfg = make_cfg(dev)
+    torch.manual_seed(SEED)                      # identical replicated weights on every rank
+    model = pc.Product2Vec(cfg).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+    # triplets: anchors are local, positives / negatives are any product of the global graph; their rows come from
+    # the owners through a row-fetch plan (built once: the index batch is fixed, as in the 1-GPU leg)
+    trip_global = torch.cat([torch.randint(0, n_loc, (TRIPLETS, 1), generator=g, device=dev) + bounds[rank],
+                             torch.randint(0, n_total, (TRIPLETS, 1 + KNEG), generator=g, device=dev)], dim=1)
+    fetch = HaloPlan(None, trip_global.reshape(-1), bounds, rank)
+    fetch.enable_peer_memory(width=128)
+    trip = fetch.col_ext.view_as(trip_global).contiguous()
+    x_host, trip_host = x.cpu().pin_memory(), trip.cpu().pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(xd, tr):
+        emb = halo_gather(forward_graph_partitioned(model, xd, plan), fetch)
+        loss = model.triplet_loss_indexed(emb, tr[:, 0], tr[:, 1], tr[:, 2:])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_gradients(model)
+        opt.step()
+        return loss
+
+    # end-to-end leg: the next step's inputs are copied from pinned host memory on a side stream while this step
+    # computes (double-buffered staging, as in the 1-GPU leg)
+    copy_stream = torch.cuda.Stream()
+    stage = [(torch.empty_like(x), torch.empty_like(trip), torch.cuda.Event()) for _ in range(2)]
+    e2e_state = {"i": 0}
+
+    def prefetch(slot):
+        xs, ts, ev = stage[slot]
+        with torch.cuda.stream(copy_stream):
+            xs.copy_(x_host, non_blocking=True)
+            ts.copy_(trip_host, non_blocking=True)
+            ev.record(copy_stream)
+
+    def step_e2e():
+        i = e2e_state["i"]
+        if i == 0:
+            prefetch(0)
+        xs, ts, ev = stage[i % 2]
+        torch.cuda.current_stream().wait_event(ev)
+        copy_stream.wait_stream(torch.cuda.current_stream())       # the other slot was last read by the previous step
+        prefetch((i + 1) % 2)
+        e2e_state["i"] = i + 1
+        loss_host.copy_(step(xs, ts).detach(), non_blocking=True)
+
+    sampler = ClockSampler(dev.index)
+    for _ in range(args.warmup):
+        step(x, trip)
+    torch.cuda.synchronize()
+    sampler.mark()
+    launches0 = _lib.LAUNCHES
+    ms, loss = timed_steps(lambda: step(x, trip), args.steps, dev, world)
+    launches = _lib.LAUNCHES - launches0
+    clocks = sampler.stop()
+    # where the step goes: CUDA events around every C-ABI call of two more steps (the difference to ms_per_step is
+    # exchange time that compute did not hide, plus the optimiser and index plumbing)
+    _lib.PROFILE = []
+    for _ in range(2):
+        step(x, trip)
+    torch.cuda.synchronize()
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    per = {}
+    for name, s0, s1 in prof:
+        per[name] = per.get(name, 0.0) + s0.elapsed_time(s1) / 2
+    abi_ms = {k: round(v, 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
+    for _ in range(2):
+        step_e2e()
+    e2e_ms, _ = timed_steps(step_e2e, args.steps, dev, world)
+    tot = torch.tensor([e_local, plan.n_halo, fetch.n_halo], dtype=torch.float64, device=dev)
+    dist.all_reduce(tot)
+    e_total, halo_total, fetch_total = tot.tolist()
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    algo = (3152 * e_local + 3676 * n_loc)
+    halo_bytes = int(halo_total / world) * 1024
+    push_ms = per.get("pc_halo_push")
+    return {
+        "metric": "gat_edges_per_sec_fwd_bwd", "value": e_total / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{label}: node-partitioned synthetic BPG, {n_loc} products / ~{e_loc} co-view edges per GPU x {world} GPUs, "
+                               "columns uniform over the global range, Product2Vec GAT fwd+bwd with a halo exchange of K|V rows "
+                               "(fwd) and dK|dV partials (bwd) over NVLink (transport: see halo_transport), triplet positives / "
+                               "negatives fetched from their owners, gradient all-reduce, Adam",
+                   "nodes_total": n_total, "edges_total": int(e_total), "halo_rows_per_gpu": int(halo_total / world),
+                   "halo_bytes_per_gpu_per_direction": halo_bytes,
+                   "triplet_rows_fetched_per_gpu": int(fetch_total / world), "halo_transport": transport,
+                   "halo_push_gbs": round(halo_bytes / (push_ms * 1e-3) / 1e9, 1) if push_ms and peer_ok else None,
+                   "csr_build": {"what": "distributed: all-to-all of edge keys by row owner + local radix sort / unique / CSR "
+                                         "(device time, max over ranks, exchange warmed up)",
+                                 "ms": build_ms, "edges_per_s": e_total / (build_ms * 1e-3)},
+                   "batchnorm": "synchronised (all-reduce of the [2,256] column sums)",
+                   "l2": "working set exceeds the 126 MB L2; no flush needed"},
+        "parity": parity,
+        "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "whole step per GPU against the sparse-kernel algorithmic bytes (3152 B/edge + 3676 B/node); "
+                             "the halo exchange moves halo_bytes over NVLink each way on top"},
+        "abi_ms_per_step": abi_ms, "abi_total_ms_per_step": round(sum(abi_ms.values()), 3),
+        "clocks": clocks,
+        "e2e": {"value": e_total / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": (x_host.numel() * 4 + trip_host.numel() * 8) * world, "d2h_bytes_per_step": 4 * world},
+        "gpu_launches": launches, "loss": float(loss.item()),
+    }
+
+
+# ============================================================================= C3: P-Companion joint step
+def pcompanion_leg(args, rank, world, dev, batch, cpu=False):
     """C3: P-Companion joint training step (type transition + item prediction, 0.8 item + 0.2 type hinge, Adam) on a
     frozen 1 M-product table, NUM_TYPES = 34,800 (reference default); data parallel over samples (replicated model,
     gradient all-reduce)."""
-    import torch.distributed as dist
     import pcompanion_b200 as pc
     from pcompanion_b200 import _lib
     from pcompanion_b200.distributed import allreduce_gradients
-    p, b = 1_000_000, args.batch
+    p, b = 1_000_000, batch
     cfg = make_cfg(dev)
     t = cfg.NUM_TYPES
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
@@ -269,11 +479,12 @@ def run_pcompanion(args, rank, world, dev):
     torch.manual_seed(SEED)
     model = pc.PCompanion(cfg, table).to(dev).train()
     opt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=cfg.LEARNING_RATE)
-    host = {"query_ids": torch.randint(0, p, (b,)), "query_types": torch.randint(0, t, (b,)),
-            "positive_types": torch.randint(0, t, (b, 1)), "negative_types": torch.randint(0, t, (b, 1)),
-            "positive_items": torch.randn(b, 128), "negative_items": torch.randn(b, 128)}
+    hg = torch.Generator().manual_seed(SEED + 7 + rank)
+    host = {"query_ids": torch.randint(0, p, (b,), generator=hg), "query_types": torch.randint(0, t, (b,), generator=hg),
+            "positive_types": torch.randint(0, t, (b, 1), generator=hg), "negative_types": torch.randint(0, t, (b, 1), generator=hg),
+            "positive_items": torch.randn(b, 128, generator=hg), "negative_items": torch.randn(b, 128, generator=hg)}
     host = {k: v.pin_memory() for k, v in host.items()}
-    batch = {k: v.to(dev) for k, v in host.items()}
+    bt_dev = {k: v.to(dev) for k, v in host.items()}
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def step(bt):
@@ -289,62 +500,81 @@ def run_pcompanion(args, rank, world, dev):
     def step_e2e():
         loss_host.copy_(step({k: v.to(dev, non_blocking=True) for k, v in host.items()}).detach(), non_blocking=True)
 
-    def timed(fn, steps):
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(steps):
-            fn()
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([ev0.elapsed_time(ev1) / steps], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
+    # the per-step working set (two [T,64] type tables + Adam state + [B,T] scores) fits the L2 at small batches
+    small = b * t * 4 < (512 << 20)
+    flush = L2Flush(dev) if small else None
     sampler = ClockSampler(dev.index)
-    for _ in range(args.warmup):
-        step(batch)
-    torch.cuda.synchronize()
+    t_warm, n_warm = time.perf_counter(), 0
+    while n_warm < args.warmup or time.perf_counter() - t_warm < 0.3:
+        step(bt_dev)
+        torch.cuda.synchronize()
+        n_warm += 1
     sampler.mark()
     l0 = _lib.LAUNCHES
-    ms = timed(lambda: step(batch), args.steps)
+    ms, _ = timed_steps(lambda: step(bt_dev), args.steps, dev, world, flush)
     launches = _lib.LAUNCHES - l0
     clocks = sampler.stop()
     step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        # bytes that must move per sample: the [T] similarity row is written once in forward and its (dense) gradient
-        # written + read once in backward; the [T,64] type table and its Adam state are per step, not per sample
-        algo = b * t * 4 * 3 + 5 * t * 64 * 4 * 2
-        line = {"metric": "pcompanion_samples_per_sec_fwd_loss_bwd", "value": b * world / (ms * 1e-3), "unit": "samples/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"C3: P-Companion joint step, 1M-product frozen table, {t} types, batch {b} per GPU, "
-                                       "K_t=3, alpha 0.8, Adam", "batch": b, "types": t,
-                           "l2": "similarity matrix [B,T] fp32 = %.1f GB per step" % (b * t * 4 / 1e9)},
-                "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                             "note": "whole step against the [B,T] similarity write + gradient write/read and the type-table "
-                                     "optimiser traffic; the [B,64]x[64,T] products are library fp32 GEMMs (cuBLAS), our kernels "
-                                     "do the type top-3 and both hinge losses"},
-                "cpu_baseline": None, "clocks": clocks,
-                "e2e": {"value": b * world / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * world,
-                        "d2h_bytes_per_step": 4 * world},
-                "gpu_launches": launches}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    e2e_ms, _ = timed_steps(step_e2e, args.steps, dev, world, flush)
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    # bytes that must move per step: the [B, T] similarity matrix is written once (it is part of forward()'s contract; the
+    # type loss reads two entries per row and its gradient goes to the factors), the two [T, 64] type tables are read,
+    # their dense gradients written and read, and Adam reads / writes p, m, v of both
+    algo = b * t * 4 + 2 * t * 64 * 4 * (1 + 2 + 6) + b * (128 * 4 * 3 + 3 * 128 * 4 * 2)
+    line = {"metric": "pcompanion_samples_per_sec_fwd_loss_bwd", "value": b * world / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C3: P-Companion joint step, 1M-product frozen table, {t} types, batch {b} per GPU, "
+                                   "K_t=3, alpha 0.8, Adam", "batch": b, "types": t,
+                       "l2": ("working set fits the L2: a 256 MB buffer is overwritten between timed steps (each step timed on "
+                              "its own)") if small else "similarity matrix [B,T] fp32 = %.1f GB per step; no flush needed" % (b * t * 4 / 1e9)},
+            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": algo,
+                         "note": "whole step against the [B,T] similarity write, the type-table read / gradient / Adam traffic "
+                                 "and the per-sample rows; small batches are launch-latency bound, not bandwidth bound"},
+            "cpu_baseline": cpu_baseline_pcompanion(cfg, b) if cpu else None, "clocks": clocks,
+            "e2e": {"value": b * world / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * world,
+                    "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches}
+    return line
 
 
-def run_retrieval(args, rank, world, dev):
+def cpu_baseline_pcompanion(cfg, batch, seconds=6.0):
+    from oracle import torch_port
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = 1_000_000 if batch <= 4096 else 100_000
+    g = torch.Generator().manual_seed(SEED)
+    ccfg = torch_port.default_config(NUM_TYPES=cfg.NUM_TYPES)
+    model = torch_port.PortPCompanion(ccfg, torch.randn(p, 128, generator=g)).train()
+    opt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=1e-3)
+    b = min(batch, 4096)
+    t = cfg.NUM_TYPES
+    qi, qt = torch.randint(0, p, (b,), generator=g), torch.randint(0, t, (b,), generator=g)
+    pt, nt = torch.randint(0, t, (b,), generator=g), torch.randint(0, t, (b,), generator=g)
+    pi, ni = torch.randn(b, 128, generator=g), torch.randn(b, 128, generator=g)
+
+    def one():
+        out = model(qi, qt)
+        loss = model.loss(out, pt, nt, pi, ni)
+        opt.zero_grad(); loss.backward(); opt.step()
+    one()
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds and n < 200:
+        one(); n += 1
+    dt = time.perf_counter() - t0
+    return {"value": b * n / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{n} steps of batch {b} through the torch-CPU port of the reference PCompanion (forward + compute_loss + "
+                      f"backward + Adam, {t} types, {p}-product table); {dt:.1f} s"}
+
+
+# ============================================================================= C4: complementary retrieval
+def retrieval_leg(args, rank, world, dev, dense=False, cpu=False):
     """C4: masked top-10 over a 10 M-product catalog (sharded over the ranks), 1 K types, Q queries x 3 type rows."""
-    import torch.distributed as dist
+    dist = _dist()
     import pcompanion_b200 as pc
     from pcompanion_b200 import _lib
     p_total, n_types, q_n, k = 10_000_000, 1000, args.queries, 10
@@ -358,69 +588,218 @@ def run_retrieval(args, rank, world, dev):
     queries = torch.randn(q_n * 3, 128, generator=gq, device=dev)
     row_type = torch.randint(0, n_types, (q_n * 3,), generator=gq, device=dev, dtype=torch.int32)
     q_host, t_host = queries.cpu().pin_memory(), row_type.cpu().pin_memory()
-    if args.dense:   # north_star wording: dense tensor-core scoring GEMM + mask + top-K (exact after fp64 re-scoring)
+    i_host = torch.empty(q_n * 3, k, dtype=torch.int64).pin_memory()
+    s_host = torch.empty(q_n * 3, k, dtype=torch.float64).pin_memory()
+    if dense:   # north_star wording: dense tensor-core scoring GEMM + mask + top-K (exact after fp64 re-scoring)
+        assert world == 1, "retrieval_dense is a single-GPU measurement"
+        cat.local.topk_dense(queries[:128], k, row_type[:128])      # max-norm of the catalog is computed once, outside the timing
         topk = lambda qq, kk, tt: cat.local.topk_dense(qq, kk, tt)
-        assert world == 1, "--dense is a single-GPU measurement"
     else:
         topk = cat.topk
+
+    def step():
+        return topk(queries, k, row_type)
+
+    def step_e2e():
+        qd = torch.empty_like(queries); qd.copy_(q_host, non_blocking=True)
+        td = torch.empty_like(row_type); td.copy_(t_host, non_blocking=True)
+        s, i = topk(qd, k, td)
+        i_host.copy_(i, non_blocking=True)
+        s_host.copy_(s, non_blocking=True)
+
     # a step is only a few ms: warm up for at least W steps AND ~0.5 s, so that the timed region does not start on a GPU
     # that is still ramping its clocks after the host-side setup
     sampler = ClockSampler(dev.index)
     t_warm, n_warm = time.perf_counter(), 0
     while n_warm < args.warmup or time.perf_counter() - t_warm < 0.5:
-        topk(queries, k, row_type)
+        step()
         torch.cuda.synchronize()
         n_warm += 1
-    if world > 1:
-        dist.barrier()
     sampler.mark()
     launches0 = _lib.LAUNCHES
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        s, i = topk(queries, k, row_type)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / args.steps
+    _lib.PROFILE = []
+    ms, _ = timed_steps(step, args.steps, dev, world)
+    prof, _lib.PROFILE = _lib.PROFILE, None
     launches = _lib.LAUNCHES - launches0
     clocks = sampler.stop()
-    ev0.record()
-    for _ in range(args.steps):
-        qd = torch.empty_like(queries); qd.copy_(q_host, non_blocking=True)
-        td = torch.empty_like(row_type); td.copy_(t_host, non_blocking=True)
-        s, i = topk(qd, k, td)
-        i_host = i.cpu()
-    ev1.record()
-    torch.cuda.synchronize()
-    e2e_ms = ev0.elapsed_time(ev1) / args.steps
-    t = torch.tensor([ms, e2e_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = t.tolist()
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        scored = q_n * 3 * (p_total / n_types)          # (row, product) pairs actually scored
-        bytes_read = scored * 512
-        line = {"metric": "topk_queries_per_sec", "value": q_n / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C4: top-10 over 10M-product catalog, 1K types, {q_n} queries x 3 type rows, "
-                                       f"catalog sharded over {world} GPU(s), " + ("dense tcgen05 TF32 scoring GEMM + per-type mask + "
-                                       "fused candidate top-K + exact fp64 re-scoring" if args.dense else "type-segmented exact fp64 scoring")},
-                "roofline": {"bound": "hbm", "achieved": bytes_read / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": bytes_read / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                             "note": "algorithmic bytes = 512 B per (row, product of the row's type) pair"},
-                "clocks": clocks,
-                "e2e": {"value": q_n / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": q_host.numel() * 4 + t_host.numel() * 4,
-                        "d2h_bytes_per_step": q_n * 3 * k * 8},
-                "gpu_launches": launches}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    step_e2e()
+    e2e_ms, _ = timed_steps(step_e2e, args.steps, dev, world)
+    per_call = {}
+    for name, s0, s1 in prof:
+        per_call[name] = per_call.get(name, 0.0) + s0.elapsed_time(s1) / args.steps
+    # algorithmic traffic of the segmented kernel on THIS rank's shard: rows that rank the same type are grouped eight at
+    # a time and a group streams its type's run of catalog rows once
+    counts = torch.bincount(row_type.long().cpu(), minlength=n_types)
+    seg_len = (cat.local.offsets[1:] - cat.local.offsets[:-1]).cpu()
+    groups = (counts + 7) // 8
+    stream_bytes = int((groups * seg_len).sum().item()) * 512 + q_n * 3 * 512 + q_n * 3 * k * 16
+    pair_flop = int((counts * seg_len).sum().item()) * 256                        # fp64 FMAs x 2 on this shard
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    if dense:
+        kms = per_call.get("pc_score_topk_dense", ms)
+        tpeak, tsrc = measured_tensor_peak()
+        tflops = q_n * 3 * per * 256 / (kms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "pc_score_topk_dense (score_topk_tf32_kernel + rescore_topk_kernel)",
+                    "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak, "traffic": None,
+                    "kernel_ms": kms, "peak_source": tsrc,
+                    "algorithmic_flop_per_launch": q_n * 3 * per * 256,
+                    "note": "256 flop per (score row, product) over the WHOLE catalog (SURVEY 8d); 99.9 % of the pairs are then "
+                            "masked out by the per-type filter, which is why the type-segmented kernel is the default"}
+    else:
+        kms = per_call.get("pc_topk_by_type", ms)
+        gbs = stream_bytes / (kms * 1e-3) / 1e9
+        f64 = pair_flop / (kms * 1e-3) / 1e12
+        roofline = {"bound": "hbm", "kernel": "pc_topk_by_type (topk_planned_kernel)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                    "frac": gbs / peak, "traffic": None, "kernel_ms": kms, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": stream_bytes,
+                    "fp64": {"achieved_tflops": f64, "peak_tflops_nominal": FP64_TFLOPS_NOMINAL, "frac": f64 / FP64_TFLOPS_NOMINAL,
+                             "note": "exact scores: one fp64 FMA per (row, product of its type, dim)"},
+                    "note": "bytes = catalog rows streamed once per group of <= 8 same-type score rows on rank 0's shard + queries "
+                            "+ results; neither HBM nor the fp64 pipe is saturated: the kernel is bound by the fp32->fp64 "
+                            "conversions and the sequential fp64 chains that make the scores order-independent"}
+    line = {"metric": "topk_queries_per_sec", "value": q_n / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4: top-10 over 10M-product catalog, 1K types, {q_n} queries x 3 type rows, "
+                                   f"catalog sharded over {world} GPU(s), " + ("dense tcgen05 TF32 scoring GEMM + per-type mask + "
+                                   "fused candidate top-K + exact fp64 re-scoring" if dense else "type-segmented exact fp64 scoring "
+                                   "(device-side grouping), per-shard lists all-gathered and merged"),
+                       "l2": "the catalog (5.12 GB per 10M rows) exceeds the 126 MB L2; no flush needed"},
+            "roofline": roofline, "abi_ms_per_step": {n_: round(v, 4) for n_, v in sorted(per_call.items(), key=lambda kv: -kv[1])},
+            "cpu_baseline": cpu_baseline_retrieval() if cpu else None,
+            "clocks": clocks,
+            "e2e": {"value": q_n / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": q_host.numel() * 4 + t_host.numel() * 4, "d2h_bytes_per_step": q_n * 3 * k * 16},
+            "gpu_launches": launches}
+    return line
 
 
-# ----------------------------------------------------------------------------- CPU baseline / reference arm
+def cpu_baseline_retrieval(steps=5, warmup=1):
+    """inference.py:93-113 semantics on the host cores: dense fp32 matmul + type mask + topk(10) on a 1 M-product sample of
+    the catalog, scaled linearly to 10 M."""
+    from oracle import torch_port
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(SEED)
+    p_sample, n_types, k, rows = 1_000_000, 1000, 10, 96
+    catalog = torch.randn(p_sample, 128, generator=g)
+    type_id = torch.randint(0, n_types, (p_sample,), generator=g)
+    q = torch.randn(rows, 128, generator=g)
+    rt = torch.randint(0, n_types, (rows,), generator=g)
+    for _ in range(warmup):
+        torch_port.port_dense_topk(q, catalog, rt, type_id, k)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        torch_port.port_dense_topk(q, catalog, rt, type_id, k)
+    dt = (time.perf_counter() - t0) / steps
+    qps = rows / 3 / dt / 10.0
+    return {"value": qps, "unit": "queries/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "ms_per_step": dt * 1e3,
+            "sample": f"{steps} x (96 score rows x 1M-product sample): dense fp32 matmul + type mask + topk(10), scaled x1/10 to the 10M catalog"}
+
+
+# ============================================================================= C1: the reference's own training flow
+def c1_leg(args, dev, cpu=False):
+    """configs[0]: the `python train.py` flow on the default synthetic BPG (1000 products, 20 types, B = 256) through the
+    drop-in classes: SimilarityDataset + collate_fn + Product2Vec.train_model-style epochs (forward(features, neighbors),
+    triplet loss, Adam), then generate_all_embeddings.  Reported as Product2Vec epoch time and padded edges/s."""
+    import pcompanion_b200 as pc
+    from pcompanion_b200 import _lib
+    from torch.utils.data import DataLoader
+    cfg = make_cfg(dev)
+    bpg = c1_bpg(dev)
+    ds = pc.SimilarityDataset(bpg, cfg)
+    loader = DataLoader(ds, batch_size=256, shuffle=True, collate_fn=pc.collate_fn, num_workers=0)
+    torch.manual_seed(SEED)
+    model = pc.Product2Vec(cfg).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+
+    def epoch():
+        model.train()
+        edges = 0
+        t_data = t_compute = 0.0
+        t0 = time.perf_counter()
+        for batch in loader:
+            t1 = time.perf_counter(); t_data += t1 - t0
+            batch = {k: v.to(dev) if isinstance(v, torch.Tensor) else v for k, v in batch.items()}
+            nb = batch.get("anchor_neighbors")
+            a = model(batch["anchor"], nb)
+            p_ = model(batch["positive"])
+            n_ = model(batch["negative"])
+            loss = model.triplet_loss(a, p_, n_)
+            opt.zero_grad(); loss.backward(); opt.step()
+            if nb is not None:
+                edges += nb.shape[0] * nb.shape[1]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter(); t_compute += t0 - t1
+        return edges, t_data, t_compute, float(loss.item())
+
+    epoch()
+    l0 = _lib.LAUNCHES
+    t0 = time.perf_counter()
+    edges, t_data, t_compute, loss = epoch()
+    dt = time.perf_counter() - t0
+    launches = _lib.LAUNCHES - l0
+    t0 = time.perf_counter()
+    emb = model.generate_all_embeddings(bpg)
+    gen_s = time.perf_counter() - t0
+    line = {"metric": "c1_product2vec_epoch_padded_edges_per_sec", "value": edges / dt, "unit": "edges/s", "n_gpus": 1,
+            "epoch_s": dt, "data_s": t_data, "compute_s": t_compute, "samples": len(ds), "padded_edges": edges, "loss": loss,
+            "generate_all_embeddings_s": gen_s, "embeddings": len(emb), "gpu_launches": launches,
+            "config": {"workload": "C1: train.py flow on the default synthetic BPG (1000 products, 20 types), B=256, drop-in "
+                                   "SimilarityDataset / collate_fn / Product2Vec.forward(features, neighbors) / Adam; wall clock "
+                                   "including the host-side data path, as the reference's own epoch"},
+            "cpu_baseline": None}
+    if cpu:
+        line["cpu_baseline"] = cpu_baseline_c1(bpg, ds, cfg)
+    return line
+
+
+def c1_bpg(dev):
+    """The reference's default synthetic BPG: edge sets produced by the real generator (src/data/synthetic_data.py:78-153,
+    written by tests/golden/make_golden.py into tests/golden/bpg_c1.npz), rebuilt through the reference's string API."""
+    import numpy as np
+    import pcompanion_b200 as pc
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "bpg_c1.npz"), allow_pickle=False))
+    n = len(g["type_id"])
+    ids = [f"P{str(i).zfill(6)}" for i in range(n)]
+    gen = torch.Generator().manual_seed(0)
+    bpg = pc.BehaviorProductGraph(dev)
+    for i, pid in enumerate(ids):
+        bpg.add_node(pid, {"type": str(g["type_names"][g["type_id"][i]]), "features": torch.randn(128, generator=gen)})
+    for t in ("co_view", "purchase_after_view", "co_purchase"):
+        for s_, d_ in g["edges/" + t]:
+            bpg.add_edge(ids[s_], ids[d_], t)
+    bpg.finalize()
+    bpg.derive_pair_sets()
+    return bpg
+
+
+def cpu_baseline_c1(bpg, ds, cfg):
+    """The same epoch through the torch-CPU port of the reference modules (same batches: our datasets are drop-ins)."""
+    import pcompanion_b200 as pc
+    from oracle import torch_port
+    from torch.utils.data import DataLoader
+    torch.set_num_threads(os.cpu_count() or 1)
+    loader = DataLoader(ds, batch_size=256, shuffle=True, collate_fn=pc.collate_fn, num_workers=0)
+    torch.manual_seed(SEED)
+    model = torch_port.PortProduct2Vec(torch_port.default_config(DROPOUT=cfg.DROPOUT)).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    edges = 0
+    t0 = time.perf_counter()
+    for batch in loader:
+        loss = torch_port.port_triplet_loss(model, batch, cfg.MARGIN)
+        opt.zero_grad(); loss.backward(); opt.step()
+        nb = batch.get("anchor_neighbors")
+        if nb is not None:
+            edges += nb.shape[0] * nb.shape[1]
+    dt = time.perf_counter() - t0
+    return {"value": edges / dt, "unit": "edges/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "epoch_s": dt, "sample": "one epoch of the same C1 batches through the torch-CPU port of the reference Product2Vec"}
+
+
+# ============================================================================= CSR build / CPU baselines of the GAT leg
 def time_csr_build(graph, peak, reps: int = 3):
     """Part (1) of the path on its own: shuffled (src, dst) edge list -> pack, radix sort, unique, CSR, then the
     transposed lists (CSC) - device time from CUDA events.  SURVEY 8(d): ~100 algorithmic bytes per edge for the CSR
@@ -493,6 +872,7 @@ def cpu_gat_sample(feats, rowptr, col, cfg, seconds, batch=4096, max_batches=64)
 
 
 def cpu_baseline_gat(bpg, graph, cfg, seconds):
+    torch.set_num_threads(os.cpu_count() or 1)
     feats = bpg.features.cpu()
     rowptr, col = graph.rowptr.cpu(), graph.col.cpu()
     real, padded, nb, dt = cpu_gat_sample(feats, rowptr, col, cfg, seconds)
@@ -503,36 +883,91 @@ def cpu_baseline_gat(bpg, graph, cfg, seconds):
                       f"edges ({padded}), real edges {real} -> {real / dt:.0f} real edges/s; {dt:.1f} s"}
 
 
+# ============================================================================= our arm
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        _dist().init_process_group("nccl", device_id=dev)
+    import pcompanion_b200  # noqa: F401  (fails loudly without the CUDA library)
+    cpu = (world == 1) and not args.skip_cpu
+    wl = args.workload
+
+    def free():
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    line = None
+    if wl in ("all", "gat"):
+        line = gat_single(args, dev) if world == 1 else gat_partitioned(args, rank, world, dev)
+        free()
+    if wl == "c5":     # BASELINE configs[4] as specified: the fixed 10 M-product / 200 M-edge graph over the ranks (strong scaling)
+        assert world > 1, "c5 is a multi-GPU configuration"
+        line = gat_partitioned(args, rank, world, dev, 10_000_000 // world, 200_000_000 // world,
+                               "C5 (fixed 10M products / 200M edges, strong scaling)")
+        if line is not None:
+            line["scaling"] = "strong"
+    if wl in ("all", "retrieval"):
+        r = retrieval_leg(args, rank, world, dev, dense=False, cpu=cpu)
+        free()
+        if wl == "retrieval":
+            line = r
+        elif line is not None:
+            line["retrieval"] = r
+            line["topk_queries_per_sec"] = r["value"]
+    if wl in ("all", "retrieval_dense") and world == 1:
+        r = retrieval_leg(args, rank, world, dev, dense=True, cpu=False)
+        free()
+        if wl == "retrieval_dense":
+            line = r
+        elif line is not None:
+            line["retrieval_dense"] = r
+    if wl in ("all", "pcompanion"):
+        batches = [256, 65536] if wl == "all" else [args.batch]
+        recs = {}
+        for b in batches:
+            recs[f"b{b}"] = pcompanion_leg(args, rank, world, dev, b, cpu=cpu and b <= 4096)
+            free()
+        if wl == "pcompanion":
+            line = recs[f"b{args.batch}"]
+        elif line is not None:
+            line["pcompanion"] = recs
+    if wl in ("all", "c1") and world == 1:
+        r = c1_leg(args, dev, cpu=cpu)
+        free()
+        if wl == "c1":
+            line = r
+        elif line is not None:
+            line["c1"] = r
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        _dist().barrier()
+        _dist().destroy_process_group()
+
+
+# ============================================================================= reference arm
 def run_reference(args):
     """The reference's own CPU path (torch-CPU port in oracle/torch_port.py; the reference is pure
-    Python/PyTorch and cannot travel to the GPU box) on the host cores, same workload."""
+    Python/PyTorch and cannot travel to the GPU box) on the host cores, same workload.  Under torchrun the launcher
+    exports OMP_NUM_THREADS=1: the thread count is reset to all host cores here."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)
     cfg = make_cfg(torch.device("cpu"))
-    if args.workload == "retrieval":
-        from oracle import torch_port
-        g = torch.Generator().manual_seed(SEED)
-        p_sample, n_types, k = 1_000_000, 1000, 10
-        catalog = torch.randn(p_sample, 128, generator=g)
-        type_id = torch.randint(0, n_types, (p_sample,), generator=g)
-        rows = 96
-        q = torch.randn(rows, 128, generator=g)
-        rt = torch.randint(0, n_types, (rows,), generator=g)
-        for _ in range(args.warmup):
-            torch_port.port_dense_topk(q, catalog, rt, type_id, k)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            torch_port.port_dense_topk(q, catalog, rt, type_id, k)
-        dt = (time.perf_counter() - t0) / args.steps
-        qps = rows / 3 / dt / 10.0   # 1 M-row sample, scaled linearly to the 10 M catalog
-        line = {"impl": "reference", "metric": "topk_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+    if args.workload in ("retrieval", "retrieval_dense"):
+        cb = cpu_baseline_retrieval(steps=args.steps, warmup=args.warmup)
+        line = {"impl": "reference", "metric": "topk_queries_per_sec", "value": cb["value"], "unit": "queries/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "C4 sample: torch matmul + type mask + topk(10), 96 rows x 1M-product sample, scaled x1/10 to 10M"},
-                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": "96 score rows x 1M products per step, dense fp32 matmul+mask+topk"},
-                "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
     # GAT: destinations of a C2-like graph (uniform random neighbours, Poisson(20) degrees); the CPU sample only
@@ -581,6 +1016,10 @@ def run_reference(args):
                              "kind": "port", "sample": f"{args.steps} steps x 2 batches x 4096 destinations; padded edges {padded}, "
                                                        f"real edges {real} ({real / dt:.0f} real edges/s)"},
             "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.workload == "all":      # second half of the metric on the host cores (bounded sample)
+        cb = cpu_baseline_retrieval(steps=3, warmup=1)
+        line["retrieval"] = {"metric": "topk_queries_per_sec", "value": cb["value"], "unit": "queries/s", "cpu_baseline": cb}
+        line["topk_queries_per_sec"] = cb["value"]
     print(json.dumps(line))
 
 
@@ -590,12 +1029,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gat", choices=["gat", "retrieval", "pcompanion"])
+    ap.add_argument("--workload", default="all", choices=["all", "gat", "retrieval", "retrieval_dense", "pcompanion", "c1", "c5"])
     ap.add_argument("--batch", type=int, default=4096, help="pcompanion: samples per GPU per step")
     ap.add_argument("--queries", type=int, default=4096)
-    ap.add_argument("--skip-cpu", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
-    ap.add_argument("--dense", action="store_true", help="retrieval: dense tcgen05 scoring + mask + top-K instead of the segmented kernel")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the CPU-baseline legs (profiling runs)")
+    ap.add_argument("--dense", action="store_true", help="(compat) with --workload retrieval: same as --workload retrieval_dense")
     args = ap.parse_args()
+    if args.dense and args.workload == "retrieval":
+        args.workload = "retrieval_dense"
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)      # timing rule: at least 3 untimed warm-up steps (reported as run)
     if args.impl == "reference":

@@ -192,6 +192,17 @@ int pc_topk_groups(const float* q, int64_t rows, int dim, const float* catalog, 
                    const int32_t* row_ids, const int32_t* grp_begin, const int64_t* seg_begin, const int64_t* seg_end,
                    int64_t n_groups, int k, int splits, int64_t index_base, double* out_scores, int64_t* out_idx,
                    void* workspace, size_t workspace_bytes, pc_stream_t stream);
+/* Same ranking with the grouping done on the device (no host read-back between the query upload and the result):
+ * row r ranks members[type_offsets[t] .. type_offsets[t+1]) for t = row_type[r] (row_type NULL: every row ranks
+ * type 0, i.e. pass n_types = 1 and type_offsets = {0, P} for an unrestricted ranking); a row_type outside
+ * [0, n_types) gives an all-padding row, as `if not type_products: continue` of inference.py:97-98.  Internally:
+ * keys type << 32 | row, stable radix sort on the type bytes (pc_sort_keys), one pass that marks every eighth
+ * row of a type's run as the start of a group, then the pc_topk_groups kernel with one CTA row per position. */
+size_t pc_topk_by_type_workspace_bytes(int64_t rows, int k, int splits);
+int pc_topk_by_type(const float* q, int64_t rows, int dim, const float* catalog, const int32_t* members,
+                    const int64_t* type_offsets, int n_types, const int32_t* row_type, int k, int splits,
+                    int64_t index_base, double* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                    pc_stream_t stream);
 /* Dense whole-catalog variant on the tensor cores (north_star part 4): scores = Q . C^T as a TF32 tcgen05
  * GEMM (never materialised; approximate scores only select candidates), per-type mask (type_id[p] == row_type[r]; row_type NULL or < 0 = no mask) and a
  * per-row candidate list fused into the epilogue, then exact float64 re-scoring + ranking of the candidates.

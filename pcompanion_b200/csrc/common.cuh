@@ -35,6 +35,16 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 int sm_count();
 
+// true the first time it is called for the CURRENT device with this flag array (per-kernel, per-device one-time setup such
+// as cudaFuncSetAttribute: a process may drive several GPUs)
+static inline bool first_use_on_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

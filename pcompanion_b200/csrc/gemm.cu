@@ -679,11 +679,9 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
     PC_REQUIRE(reinterpret_cast<uintptr_t>(aux) % 16 == 0, PC_ERR_INVALID, "linear: aux must be 16-byte aligned (TMA)");
     if (int rc = make_map(&map_aux, aux, m, n, ld_aux, BM)) return rc;
   }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (first_use_on_device(configured))
     PC_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    configured = true;
-  }
   const int64_t tiles = ((m + BM - 1) / BM) * p.n_tiles;
   const int grid = int(tiles < sm_count() ? tiles : sm_count());
   linear_tf32x3_kernel<<<grid, LIN_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out0, map_out1, map_aux, p);
@@ -732,11 +730,9 @@ extern "C" int pc_wgrad_tf32x3(const float* dy, int64_t m, int n, int64_t ld_dy,
   if (int rc = make_map_mn(&map_dy, dy, m, n, ld_dy, 4)) return rc;
   if (int rc = make_map_mn(&map_x, x, m, k, ld_x, k / 32)) return rc;
   if (int rc = make_map(&map_pw, p.partial_w, int64_t(subsets) * n, k, k, BM)) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (first_use_on_device(configured))
     PC_CUDA(cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-    configured = true;
-  }
   cudaStream_t st = as_stream(stream);
   wgrad_tf32x3_kernel<<<grid, GEMM_THREADS, WG_SMEM, st>>>(map_dy, map_x, map_pw, p);
   PC_LAUNCH_CHECK();

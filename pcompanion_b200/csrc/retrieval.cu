@@ -81,25 +81,20 @@ __device__ __forceinline__ void stage_chunk(float* tile, const float* __restrict
 // members[seg_begin[g] .. seg_end[g]).  Lane = one product of a 32-product batch; 32-dim chunks are staged
 // through shared memory with cp.async (double-buffered, coalesced), then every lane advances RB independent
 // sequential fp64 dot products (the RB chains interleave, which is what keeps the fp64 pipe busy).
-__global__ void __launch_bounds__(TK_WARPS * 32)
-topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
-                   const int32_t* __restrict__ members, const int32_t* __restrict__ row_ids,
-                   const int32_t* __restrict__ grp_begin, const int64_t* __restrict__ seg_begin,
-                   const int64_t* __restrict__ seg_end, int k, int splits, int64_t index_base,
-                   double* __restrict__ part_s, int64_t* __restrict__ part_i) {
+__device__ __forceinline__ void topk_group_body(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
+                                                const int32_t* __restrict__ members, const int32_t* __restrict__ row_ids,
+                                                int r_beg, int n_rows, int64_t beg, int64_t end, int k, int splits, int split,
+                                                int64_t index_base, double* __restrict__ part_s, int64_t* __restrict__ part_i) {
   extern __shared__ double smem_d[];
   double* q_s = smem_d;                                                      // [RB][dim], rows >= n_rows are zero
   float* tiles = reinterpret_cast<float*>(q_s + RB * dim);                   // [TK_WARPS][2][32][TILE_LD]
   Cand* lists = reinterpret_cast<Cand*>(tiles + TK_WARPS * 2 * TILE_FLOATS); // [TK_WARPS][RB][32]
   const int lane = lane_id(), w = warp_id();
-  const int g = blockIdx.y, split = blockIdx.x;
-  const int r_beg = grp_begin[g], n_rows = grp_begin[g + 1] - r_beg;
   for (int i = threadIdx.x; i < RB * dim; i += blockDim.x) {
     const int r = i / dim, d = i - r * dim;
     q_s[i] = r < n_rows ? double(Q[int64_t(row_ids[r_beg + r]) * dim + d]) : 0.0;
   }
   __syncthreads();
-  const int64_t beg = seg_begin[g], end = seg_end[g];
   const int64_t len = end > beg ? end - beg : 0;
   const int64_t per = (ceil_div(len, int64_t(splits)) + 31) / 32 * 32;
   const int64_t sb = beg + per * split;
@@ -188,6 +183,67 @@ topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict
       part_i[o] = best.i;
     }
   }
+}
+
+__global__ void __launch_bounds__(TK_WARPS * 32)
+topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
+                   const int32_t* __restrict__ members, const int32_t* __restrict__ row_ids,
+                   const int32_t* __restrict__ grp_begin, const int64_t* __restrict__ seg_begin,
+                   const int64_t* __restrict__ seg_end, int k, int splits, int64_t index_base,
+                   double* __restrict__ part_s, int64_t* __restrict__ part_i) {
+  const int g = blockIdx.y;
+  const int r_beg = grp_begin[g];
+  topk_group_body(Q, dim, catalog, members, row_ids, r_beg, grp_begin[g + 1] - r_beg, seg_begin[g], seg_end[g], k, splits,
+                  int(blockIdx.x), index_base, part_s, part_i);
+}
+
+// ---- device-side grouping (pc_topk_by_type): no host read-back anywhere between the query upload and the result.
+// keys[r] = type(r) << 32 | r (type = n_types for rows without a valid type: an empty run); after a stable sort on the
+// type bytes, rows of one type are adjacent and ascending.  plan: position p starts a group iff its rank inside
+// its type's run is a multiple of RB; grp_rows[p] = rows in that group (0 elsewhere).  The ranking kernel is
+// launched with one CTA row per POSITION; the 7 of 8 (or more) CTAs that do not start a group return at once.
+__global__ void type_keys_kernel(const int32_t* __restrict__ row_type, int64_t rows, int n_types, uint64_t* __restrict__ keys) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int t = row_type ? row_type[r] : 0;
+  if (t < 0 || t >= n_types) t = n_types;
+  keys[r] = (uint64_t(uint32_t(t)) << 32) | uint64_t(uint32_t(r));
+}
+
+__global__ void topk_plan_kernel(const uint64_t* __restrict__ keys, int64_t rows, int32_t* __restrict__ row_ids,
+                                 int32_t* __restrict__ grp_rows) {
+  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= rows) return;
+  const uint64_t key = keys[p];
+  const uint64_t t = key >> 32;
+  row_ids[p] = int32_t(uint32_t(key));
+  int64_t lo = 0, hi = p;                       // first position whose type is t
+  const uint64_t want = t << 32;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < want) lo = mid + 1; else hi = mid;
+  }
+  int n = 0;
+  if (((p - lo) % RB) == 0) {
+    n = 1;
+    while (n < RB && p + n < rows && (keys[p + n] >> 32) == t) ++n;
+  }
+  grp_rows[p] = n;
+}
+
+__global__ void __launch_bounds__(TK_WARPS * 32)
+topk_planned_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
+                    const int32_t* __restrict__ members, const int32_t* __restrict__ row_ids,
+                    const int32_t* __restrict__ grp_rows, const uint64_t* __restrict__ keys,
+                    const int64_t* __restrict__ type_offsets, int n_types, int64_t p0, int k, int splits,
+                    int64_t index_base, double* __restrict__ part_s, int64_t* __restrict__ part_i) {
+  const int64_t p = p0 + blockIdx.y;
+  const int n_rows = grp_rows[p];
+  if (n_rows == 0) return;                      // uniform over the CTA
+  const int64_t t = int64_t(keys[p] >> 32);
+  const int64_t beg = t < n_types ? type_offsets[t] : 0, end = t < n_types ? type_offsets[t + 1] : 0;
+  topk_group_body(Q, dim, catalog, members, row_ids, int(p), n_rows, beg, end, k, splits, int(blockIdx.x), index_base,
+                  part_s, part_i);
 }
 
 // row-wise top-k of a materialised fp32 matrix: grid = (splits, rows)
@@ -289,11 +345,7 @@ extern "C" int pc_topk_groups(const float* q, int64_t rows, int dim, const float
   cudaStream_t st = as_stream(stream);
   const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 2 * TILE_FLOATS * sizeof(float) +
                       size_t(TK_WARPS) * RB * 32 * sizeof(Cand);
-  static bool configured = false;
-  if (!configured) {
-    PC_CUDA(cudaFuncSetAttribute(topk_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
-  }
+  PC_CUDA(cudaFuncSetAttribute(topk_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   PC_REQUIRE(smem <= 160 * 1024, PC_ERR_UNSUPPORTED, "topk_groups: shared memory budget exceeded");
   double* ps = out_scores;
   int64_t* pi = out_idx;
@@ -308,6 +360,62 @@ extern "C" int pc_topk_groups(const float* q, int64_t rows, int dim, const float
     dim3 grid{unsigned(splits), unsigned(ng), 1u};
     topk_groups_kernel<<<grid, TK_WARPS * 32, smem, st>>>(q, dim, catalog, members, row_ids, grp_begin + g0, seg_begin + g0,
                                                           seg_end + g0, k, splits, index_base, ps, pi);
+    PC_LAUNCH_CHECK();
+  }
+  if (splits > 1) return pc_topk_merge(ps, pi, rows, splits, k, out_scores, out_idx, stream);
+  return PC_OK;
+}
+
+extern "C" size_t pc_topk_by_type_workspace_bytes(int64_t rows, int k, int splits) {
+  if (rows <= 0) return 0;
+  return align_up(size_t(rows) * 8, 256) + align_up(pc_sort_keys_workspace_bytes(rows), 256) + 2 * align_up(size_t(rows) * 4, 256) +
+         pc_topk_groups_workspace_bytes(rows, k, splits);
+}
+
+extern "C" int pc_topk_by_type(const float* q, int64_t rows, int dim, const float* catalog, const int32_t* members,
+                               const int64_t* type_offsets, int n_types, const int32_t* row_type, int k, int splits,
+                               int64_t index_base, double* out_scores, int64_t* out_idx, void* workspace,
+                               size_t workspace_bytes, pc_stream_t stream) {
+  PC_REQUIRE(rows >= 0 && rows < (int64_t(1) << 31), PC_ERR_INVALID, "topk_by_type: bad row count");
+  if (rows == 0) return PC_OK;
+  PC_REQUIRE(q && catalog && type_offsets && out_scores && out_idx && workspace, PC_ERR_INVALID, "topk_by_type: null pointer");
+  PC_REQUIRE(n_types >= 1 && n_types < (1 << 30), PC_ERR_INVALID, "topk_by_type: bad n_types=%d", n_types);
+  PC_REQUIRE(k >= 1 && k <= 32, PC_ERR_UNSUPPORTED, "topk_by_type: k=%d outside [1,32]", k);
+  PC_REQUIRE(dim >= DCH && dim % DCH == 0 && dim <= 1024, PC_ERR_UNSUPPORTED, "topk_by_type: dim=%d must be a multiple of %d (<= 1024)", dim, DCH);
+  PC_REQUIRE(splits >= 1 && splits <= 65535, PC_ERR_UNSUPPORTED, "topk_by_type: bad splits");
+  PC_REQUIRE(workspace_bytes >= pc_topk_by_type_workspace_bytes(rows, k, splits), PC_ERR_WORKSPACE, "topk_by_type: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(ws);             ws += align_up(size_t(rows) * 8, 256);
+  void* sort_ws = ws;                                            const size_t sort_bytes = pc_sort_keys_workspace_bytes(rows);
+  ws += align_up(sort_bytes, 256);
+  int32_t* row_ids = reinterpret_cast<int32_t*>(ws);             ws += align_up(size_t(rows) * 4, 256);
+  int32_t* grp_rows = reinterpret_cast<int32_t*>(ws);            ws += align_up(size_t(rows) * 4, 256);
+  const unsigned tb = unsigned(ceil_div(rows, 256));
+  type_keys_kernel<<<tb, 256, 0, st>>>(row_type, rows, n_types, keys);
+  PC_LAUNCH_CHECK();
+  // keys are created in ascending row order and the sort is stable: only the type bytes take part
+  uint32_t mask = 0;
+  for (int b = 0; b < 4; ++b)
+    if ((uint64_t(n_types) >> (8 * b)) != 0) mask |= 1u << (4 + b);
+  if (int rc = pc_sort_keys(keys, rows, mask, sort_ws, sort_bytes, stream)) return rc;
+  topk_plan_kernel<<<tb, 256, 0, st>>>(keys, rows, row_ids, grp_rows);
+  PC_LAUNCH_CHECK();
+  const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 2 * TILE_FLOATS * sizeof(float) +
+                      size_t(TK_WARPS) * RB * 32 * sizeof(Cand);
+  PC_REQUIRE(smem <= 160 * 1024, PC_ERR_UNSUPPORTED, "topk_by_type: shared memory budget exceeded");
+  PC_CUDA(cudaFuncSetAttribute(topk_planned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  double* ps = out_scores;
+  int64_t* pi = out_idx;
+  if (splits > 1) {
+    ps = reinterpret_cast<double*>(ws);
+    pi = reinterpret_cast<int64_t*>(ps + size_t(rows) * splits * k);
+  }
+  for (int64_t p0 = 0; p0 < rows; p0 += 65535) {   // gridDim.y limit
+    const int64_t np = rows - p0 < 65535 ? rows - p0 : 65535;
+    dim3 grid{unsigned(splits), unsigned(np), 1u};
+    topk_planned_kernel<<<grid, TK_WARPS * 32, smem, st>>>(q, dim, catalog, members, row_ids, grp_rows, keys, type_offsets,
+                                                           n_types, p0, k, splits, index_base, ps, pi);
     PC_LAUNCH_CHECK();
   }
   if (splits > 1) return pc_topk_merge(ps, pi, rows, splits, k, out_scores, out_idx, stream);

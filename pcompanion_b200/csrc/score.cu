@@ -352,11 +352,9 @@ extern "C" int pc_score_topk_dense(const float* q, int64_t rows, int dim, const 
   CUtensorMap map_q, map_c;
   if (int rc = make_map(&map_q, q, rows, dim, dim, BM)) return rc;
   if (int rc = make_map(&map_c, catalog, products, dim, dim, SC_BN, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (first_use_on_device(configured))
     PC_CUDA(cudaFuncSetAttribute(score_topk_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
-    configured = true;
-  }
   cudaStream_t st = as_stream(stream);
   const int64_t total_units = ((rows + BM - 1) / BM) * units;
   const int grid = int(total_units < sm_count() ? total_units : sm_count());

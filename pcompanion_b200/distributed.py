@@ -17,9 +17,7 @@ product path is CUDA.
 """
 from __future__ import annotations
 
-import json
 import os
-import time
 from typing import List, Optional
 
 import torch
@@ -318,146 +316,3 @@ def allreduce_gradients(model, group=None) -> None:
     for g in grads:
         g.copy_(flat[off: off + g.numel()].view_as(g))
         off += g.numel()
-
-
-# ----------------------------------------------------------------------------- multi-GPU benchmark leg
-def run_partitioned_bench(args, rank: int, world: int, dev: torch.device) -> None:
-    """bench.py --gpus N (N > 1): weak scaling, 1 M nodes / ~20 M edges per GPU, columns uniform over
-    the global node range, so (N-1)/N of every rank's edges point at halo rows."""
-    import bench as B
-    import pcompanion_b200 as pc
-    from pcompanion_b200 import _lib
-    n_loc, e_loc = B.NODES_PER_GPU, B.EDGES_PER_GPU
-    n_total = n_loc * world
-    bounds = [i * n_loc for i in range(world + 1)]
-    g = torch.Generator(device=dev).manual_seed(B.SEED + 100 + rank)
-    # every rank draws its share of the GLOBAL edge list; the owners of the rows get them through the distributed
-    # CSR build (one all-to-all of keys, then local sort / unique) - timed separately, outside the step
-    rows = torch.randint(0, n_total, (e_loc,), generator=g, device=dev, dtype=torch.int32)
-    cols = torch.randint(0, n_total, (e_loc,), generator=g, device=dev, dtype=torch.int32)
-    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-    rowptr, col_global = partition_edges(rows, cols, bounds, rank)
-    torch.cuda.synchronize(); dist.barrier(); build_s = time.perf_counter() - t0
-    del rows, cols
-    plan = HaloPlan(rowptr, col_global, bounds, rank)
-    plan.graph.transposed()
-    transport = ("pc_halo_push: gather + NVLink stores into the peers' symmetric-memory tables, one launch per direction"
-                 if plan.enable_peer_memory() else
-                 "NCCL all_to_all_single (" + getattr(plan, "peer_error", "peer memory disabled") + ")")
-    e_local = col_global.numel()
-    x = torch.randn(n_loc, 128, generator=g, device=dev)
-    cfg = B.make_cfg(dev)
-    torch.manual_seed(B.SEED)                      # identical replicated weights on every rank
-    model = pc.Product2Vec(cfg).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
-    # triplets: anchors are local, positives / negatives are any product of the global graph; their rows come from
-    # the owners through a row-fetch plan (built once: the index batch is fixed, as in the 1-GPU leg)
-    trip_global = torch.cat([torch.randint(0, n_loc, (B.TRIPLETS, 1), generator=g, device=dev) + bounds[rank],
-                             torch.randint(0, n_total, (B.TRIPLETS, 1 + B.KNEG), generator=g, device=dev)], dim=1)
-    fetch = HaloPlan(None, trip_global.reshape(-1), bounds, rank)
-    fetch.enable_peer_memory(width=128)
-    trip = fetch.col_ext.view_as(trip_global).contiguous()
-    x_host, trip_host = x.cpu().pin_memory(), trip.cpu().pin_memory()
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-
-    def step(xd, tr):
-        emb = halo_gather(forward_graph_partitioned(model, xd, plan), fetch)
-        loss = model.triplet_loss_indexed(emb, tr[:, 0], tr[:, 1], tr[:, 2:])
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        allreduce_gradients(model)
-        opt.step()
-        return loss
-
-    # end-to-end leg: the next step's inputs are copied from pinned host memory on a side stream while this step
-    # computes (double-buffered staging, as in the 1-GPU leg)
-    copy_stream = torch.cuda.Stream()
-    stage = [(torch.empty_like(x), torch.empty_like(trip), torch.cuda.Event()) for _ in range(2)]
-    e2e_state = {"i": 0}
-
-    def prefetch(slot):
-        xs, ts, ev = stage[slot]
-        with torch.cuda.stream(copy_stream):
-            xs.copy_(x_host, non_blocking=True)
-            ts.copy_(trip_host, non_blocking=True)
-            ev.record(copy_stream)
-
-    def step_e2e():
-        i = e2e_state["i"]
-        if i == 0:
-            prefetch(0)
-        xs, ts, ev = stage[i % 2]
-        torch.cuda.current_stream().wait_event(ev)
-        copy_stream.wait_stream(torch.cuda.current_stream())       # the other slot was last read by the previous step
-        prefetch((i + 1) % 2)
-        e2e_state["i"] = i + 1
-        loss_host.copy_(step(xs, ts).detach(), non_blocking=True)
-
-    def timed(fn, steps):
-        torch.cuda.synchronize(); dist.barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(steps):
-            out = fn()
-        ev1.record()
-        torch.cuda.synchronize(); dist.barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1) / steps], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item(), out
-
-    sampler = B.ClockSampler(dev.index)
-    for _ in range(args.warmup):
-        step(x, trip)
-    torch.cuda.synchronize()
-    sampler.mark()
-    launches0 = _lib.LAUNCHES
-    ms, loss = timed(lambda: step(x, trip), args.steps)
-    launches = _lib.LAUNCHES - launches0
-    clocks = sampler.stop()
-    # where the step goes: CUDA events around every C-ABI call of two more steps (the difference to ms_per_step is
-    # exchange time that compute did not hide, plus the optimiser and index plumbing)
-    _lib.PROFILE = []
-    for _ in range(2):
-        step(x, trip)
-    torch.cuda.synchronize()
-    prof, _lib.PROFILE = _lib.PROFILE, None
-    per = {}
-    for name, s0, s1 in prof:
-        per[name] = per.get(name, 0.0) + s0.elapsed_time(s1) / 2
-    abi_ms = {k: round(v, 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
-    for _ in range(2):
-        step_e2e()
-    e2e_ms, _ = timed(step_e2e, args.steps)
-    tot = torch.tensor([e_local, plan.n_halo, fetch.n_halo], dtype=torch.float64, device=dev)
-    dist.all_reduce(tot)
-    e_total, halo_total, fetch_total = tot.tolist()
-    if rank == 0:
-        peak, peak_src = B.measured_peaks()
-        algo = (3152 * e_local + 3676 * n_loc)
-        line = {
-            "metric": "gat_edges_per_sec_fwd_bwd", "value": e_total / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C5-style: node-partitioned synthetic BPG, {n_loc} products / ~{e_loc} co-view edges per GPU x {world} GPUs, "
-                                   "columns uniform over the global range, Product2Vec GAT fwd+bwd with NCCL all-to-all halo exchange of "
-                                   "K|V rows (fwd) and dK|dV partials (bwd), triplet positives / negatives fetched from their owners, "
-                                   "gradient all-reduce, Adam",
-                       "nodes_total": n_total, "edges_total": int(e_total), "halo_rows_per_gpu": int(halo_total / world),
-                       "halo_bytes_per_gpu_per_direction": int(halo_total / world) * 1024,
-                       "triplet_rows_fetched_per_gpu": int(fetch_total / world), "halo_transport": transport,
-                       "csr_build": {"what": "distributed: all-to-all of edge keys by row owner + local radix sort / unique / CSR",
-                                     "seconds": build_s, "edges_per_s": e_total / build_s}, "batchnorm": "synchronised (all-reduce of the [2,256] column sums)",
-                       "l2": "working set exceeds the 126 MB L2; no flush needed"},
-            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "whole step per GPU against the sparse-kernel algorithmic bytes (3152 B/edge + 3676 B/node); "
-                                 "the halo all-to-all moves halo_bytes over NVLink each way on top"},
-            "abi_ms_per_step": abi_ms, "abi_total_ms_per_step": round(sum(abi_ms.values()), 3),
-            "clocks": clocks,
-            "e2e": {"value": e_total / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": (x_host.numel() * 4 + trip_host.numel() * 8) * world, "d2h_bytes_per_step": 4 * world},
-            "gpu_launches": launches, "loss": float(loss.item()),
-        }
-        print(json.dumps(line))
-    dist.barrier()
-    dist.destroy_process_group()

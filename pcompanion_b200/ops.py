@@ -6,6 +6,7 @@ layer and nothing falls back to it.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import Optional, Tuple
 
@@ -533,6 +534,29 @@ def topk_segments(q: torch.Tensor, catalog: torch.Tensor, seg_begin: torch.Tenso
     call("pc_topk_groups", dev(q.contiguous(), F32, "q"), rows, dim, dev(catalog, F32, "catalog"),
          dev(members, I32, "members"), dev(row_ids, I32, "row_ids"), dev(grp_begin, I32, "grp_begin"),
          dev(g_beg, I64, "seg_begin"), dev(g_end, I64, "seg_end"), n_groups, k, splits, int(index_base),
+         dev(out_s, F64, "out_scores"), dev(out_i, I64, "out_idx"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return out_s, out_i
+
+
+def topk_by_type(q: torch.Tensor, catalog: torch.Tensor, type_offsets: torch.Tensor, n_types: int,
+                 row_type: Optional[torch.Tensor], k: int, members: Optional[torch.Tensor] = None, index_base: int = 0,
+                 splits: Optional[int] = None):
+    """Exact top-k of every row over the catalog rows of its type, grouping done on the device (pc_topk_by_type): no
+    host synchronisation between the inputs and the result.  Returns (scores f64 [R,k], idx i64 [R,k])."""
+    q = q.contiguous()
+    rows, dim = q.shape
+    out_s = torch.empty(rows, k, dtype=F64, device=q.device)
+    out_i = torch.empty(rows, k, dtype=I64, device=q.device)
+    if rows == 0:
+        return out_s, out_i
+    if splits is None:
+        # expected number of groups without looking at the data: distinct types hit + one more group per 8 rows
+        n_cat = members.numel() if members is not None else catalog.shape[0]
+        distinct = n_types * (1.0 - math.exp(-rows / max(n_types, 1)))
+        splits = _auto_splits(int(distinct + rows / TOPK_GROUP_ROWS) + 1, n_cat / max(n_types, 1))
+    ws = _lib.workspace(_lib.LIB.pc_topk_by_type_workspace_bytes(rows, k, splits), q.device)
+    call("pc_topk_by_type", dev(q, F32, "q"), rows, dim, dev(catalog, F32, "catalog"), dev(members, I32, "members"),
+         dev(type_offsets, I64, "type_offsets"), int(n_types), dev(row_type, I32, "row_type"), k, splits, int(index_base),
          dev(out_s, F64, "out_scores"), dev(out_i, I64, "out_idx"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
     return out_s, out_i
 

@@ -82,6 +82,7 @@ class CatalogIndex:
         self.members = None
         self.offsets = None
         self._max_norm = None
+        self._all = None
         if type_id is not None:
             self.type_id = type_id.to(catalog.device, torch.int32).contiguous()
             n_types = int(num_types) if num_types is not None else (int(self.type_id.max().item()) + 1 if self.num_products else 0)
@@ -96,19 +97,14 @@ class CatalogIndex:
         when row_type is None).  Returns (scores float64 [R, k], global indices int64 [R, k]),
         padded with (-inf, -1) when a type has fewer than k products."""
         queries = queries.contiguous().float()
-        r = queries.shape[0]
-        dev = queries.device
         if row_type is None:
-            beg = torch.zeros(r, dtype=torch.int64, device=dev)
-            end = torch.full((r,), self.num_products, dtype=torch.int64, device=dev)
-            return ops.topk_segments(queries, self.catalog, beg, end, k, None, self.index_base, splits)
+            if self._all is None:
+                self._all = torch.tensor([0, self.num_products], dtype=torch.int64, device=queries.device)
+            return ops.topk_by_type(queries, self.catalog, self._all, 1, None, k, None, self.index_base, splits)
         if self.offsets is None:
             raise ValueError("CatalogIndex.topk: the catalog was built without type ids")
-        t = row_type.to(dev, torch.int64).clamp_(0, self.num_types - 1)
-        valid = (row_type.to(dev) >= 0) & (row_type.to(dev) < self.num_types)
-        beg = torch.where(valid, self.offsets[t], torch.zeros_like(t))
-        end = torch.where(valid, self.offsets[t + 1], torch.zeros_like(t))
-        return ops.topk_segments(queries, self.catalog, beg, end, k, self.members, self.index_base, splits)
+        rt = row_type.to(queries.device, torch.int32).contiguous()
+        return ops.topk_by_type(queries, self.catalog, self.offsets, self.num_types, rt, k, self.members, self.index_base, splits)
 
     def topk_dense(self, queries: torch.Tensor, k: int, row_type: Optional[torch.Tensor] = None):
         """Same result as ``topk`` through the dense tensor-core path (BASELINE north_star part 4): single-pass TF32 scoring
