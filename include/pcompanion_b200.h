@@ -224,6 +224,42 @@ int pc_topk_rows(const float* values, int64_t rows, int64_t cols, int k, int spl
 int pc_topk_merge(const double* scores, const int64_t* idx, int64_t rows, int lists, int k, double* out_scores,
                   int64_t* out_idx, pc_stream_t stream);
 
+/* ------------------------------------------------------------------ P-Companion joint model (small dense layers)
+ * Type scoring with the row top-k fused into the GEMM epilogue (p_companion.py:60-64: comp_base @ W^T, topk(3)):
+ * scores[m, n] = A[m, k] . W[n, k]^T on the tensor cores (same fp32-faithful 3 x TF32 kernel as pc_linear_tf32x3, any n
+ * with n % 4 == 0, no bias), the best `topk` (<= 4) columns of every row tracked in the epilogue (ties -> lowest
+ * column) and merged per row.  `out` (the [m, n] matrix, row stride ld_out) may be NULL: the scores are then never
+ * written.  out_scores double [m, topk], out_idx int64 [m, topk]. */
+size_t pc_type_scores_topk_workspace_bytes(int64_t m, int n, int k, int topk);
+int pc_type_scores_topk(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, float* out, int64_t ld_out,
+                        int topk, double* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                        pc_stream_t stream);
+/* Two-layer MLP of type_transition.py:15-20 on gathered rows: x = table[idx[r]] (idx NULL: table[r]),
+ * hidden = dropout(relu(W1 x + b1)), out = W2 hidden + b2.  W1 [hid, d_in], W2 [d_out, hid] row-major (nn.Linear
+ * layout).  dropout_p in [0,1): counter-based mask from (seed, row, unit), survivors scaled by 1/(1-p) (torch's
+ * Philox stream cannot be matched; pass 0 in eval mode).  `hidden` [rows, hid] is kept for the backward. */
+int pc_mlp2_fwd(const float* table, const int64_t* idx, int64_t rows, int d_in, int hid, int d_out, const float* w1,
+                const float* b1, const float* w2, const float* b2, float dropout_p, uint64_t seed, float* hidden,
+                float* out, pc_stream_t stream);
+/* Backward: d_x [rows, d_in] (may be NULL), d_w1, d_b1, d_w2, d_b2 (each may be NULL); the weight gradients are summed
+ * per CTA in row order and then over the CTAs in CTA order (deterministic).  dropout_p as in the forward. */
+size_t pc_mlp2_bwd_workspace_bytes(int d_in, int hid, int d_out);
+int pc_mlp2_bwd(const float* d_out_rows, const float* table, const int64_t* idx, const float* hidden, int64_t rows, int d_in,
+                int hid, int d_out, const float* w1, const float* w2, float dropout_p, float* d_x, float* d_w1, float* d_b1,
+                float* d_w2, float* d_b2, void* workspace, size_t workspace_bytes, pc_stream_t stream);
+/* item_prediction.py:33-38: out[b, t, :] = pi[b, :] * tp[b * kt + t, :]  (pi = item_projection(q), tp =
+ * type_projection(T), both from pc_linear_tf32x3) and its backward d_pi = sum_t d_out * tp, d_tp = d_out * pi. */
+int pc_item_combine_fwd(const float* pi, const float* tp, int64_t rows, int kt, int dim, float* out, pc_stream_t stream);
+int pc_item_combine_bwd(const float* d_out, const float* pi, const float* tp, int64_t rows, int kt, int dim, float* d_pi,
+                        float* d_tp, pc_stream_t stream);
+/* Gradient of the type hinge (p_companion.py:95-103) with respect to the FACTORS of S = base . W^T: only S[i, pos_i] and
+ * S[i, neg_i] carry gradient, so d_base[i] = c_i (W[neg_i] - W[pos_i]) and W gets -c_i base[i] on row pos_i, +c_i base[i] on
+ * row neg_i, c_i = grad / rows where the hinge of row i is active (per_row[i] > 0) and pos_i != neg_i.  vals [2 rows, width]:
+ * slot i -> pos_i, slot rows + i -> neg_i (summed per type by pc_rows_segment_sum). */
+int pc_hinge_type_factored_bwd(const float* per_row, const int64_t* pos, const int64_t* neg, const float* grad,
+                               const float* base, const float* weight, int64_t rows, int width, float* d_base, float* vals,
+                               pc_stream_t stream);
+
 /* ------------------------------------------------------------------ multi-GPU halo helpers
  * Row gather (pack boundary K|V rows before the all-to-all) and deterministic scatter-add
  * (owner-side reduction of returned dK|dV partials in fixed peer order). width in floats, %4==0. */
@@ -252,6 +288,14 @@ int pc_halo_push(const float* table, int64_t ld, const int64_t* index, int world
  * kernels), used for the embedding rows a triplet batch touches (product2vec.py:132-134 on a shared table). */
 int pc_rows_segment_sum(const float* rows, const int64_t* rowptr, const int32_t* col, int64_t n, int width, float* out,
                         pc_stream_t stream);
+
+/* The same as ONE call from an index list: out[n_rows, width] = dense gradient of table[index] given the gradient rows
+ * [slots, width] (slot s belongs to table row index[s]); keys index << 32 | slot, stable radix sort on the row bytes,
+ * CSR, pc_rows_segment_sum.  Replaces the atomicAdd-based backward of nn.Embedding / advanced indexing
+ * (p_companion.py:54,66; product2vec.py:132-134 on a shared table) with a deterministic one. */
+size_t pc_rows_index_grad_workspace_bytes(int64_t slots, int64_t n_rows);
+int pc_rows_index_grad(const float* rows, const int64_t* index, int64_t slots, int64_t n_rows, int width, float* out,
+                       void* workspace, size_t workspace_bytes, pc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,14 @@ PROTOTYPES = {
     "pc_linear_tf32x3": (c_int, [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int64, P, P, c_int64, c_int, P, c_int64, P, c_size_t, P]),
     "pc_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pc_wgrad_tf32x3": (c_int, [P, c_int64, c_int, c_int64, P, c_int, c_int64, P, P, P, c_size_t, P]),
+    "pc_type_scores_topk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
+    "pc_type_scores_topk": (c_int, [P, c_int64, c_int, c_int64, P, c_int, P, c_int64, c_int, P, P, P, c_size_t, P]),
+    "pc_mlp2_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_uint64, P, P, P]),
+    "pc_mlp2_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pc_mlp2_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, P, P, c_float, P, P, P, P, P, P, c_size_t, P]),
+    "pc_item_combine_fwd": (c_int, [P, P, c_int64, c_int, c_int, P, P]),
+    "pc_item_combine_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P]),
+    "pc_hinge_type_factored_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int, P, P, P]),
     "pc_hinge_rows_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_float, c_float, P, P, P]),
     "pc_hinge_rows_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]),
     "pc_hinge_type_fwd": (c_int, [P, P, P, c_int64, c_int64, c_float, P, P, P]),
@@ -62,6 +70,8 @@ PROTOTYPES = {
     "pc_rows_scatter_add": (c_int, [P, P, c_int64, c_int, P, P]),
     "pc_rows_reduce_peers": (c_int, [P, P, c_int, c_int64, c_int, P, P]),
     "pc_halo_push": (c_int, [P, c_int64, P, c_int, P, P, P, P, c_int64, c_int, P]),
+    "pc_rows_index_grad_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "pc_rows_index_grad": (c_int, [P, P, c_int64, c_int64, c_int, P, P, c_size_t, P]),
     "pc_rows_segment_sum": (c_int, [P, P, P, c_int64, c_int, P, P]),
 }
 

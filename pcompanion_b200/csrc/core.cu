@@ -77,6 +77,12 @@ rows_segment_sum_kernel(const float4* __restrict__ rows, const int64_t* __restri
   }
 }
 
+// keys[s] = index[s] << 32 | s: a stable sort on the index bytes groups the slots of one table row, slots ascending
+__global__ void index_slot_keys_kernel(const int64_t* __restrict__ index, int64_t n, uint64_t* __restrict__ keys) {
+  const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s < n) keys[s] = (uint64_t(index[s]) << 32) | uint64_t(uint32_t(s));
+}
+
 // table[r, :] += sum over peers p = 0..world-1 (in that order) of rows[slot[p * n + r], :] where slot >= 0: the
 // owner-side reduction of returned halo partials as ONE pass over the local rows (fixed order => deterministic).
 __global__ void __launch_bounds__(256)
@@ -220,4 +226,43 @@ extern "C" int pc_rows_segment_sum(const float* rows, const int64_t* rowptr, con
       reinterpret_cast<const float4*>(rows), rowptr, col, n, width / 4, reinterpret_cast<float4*>(out));
   PC_LAUNCH_CHECK();
   return PC_OK;
+}
+
+
+// Dense gradient of a row gather table[index] without float atomics, as ONE call: slots keyed by table row, stable radix
+// sort on the row bytes, CSR over the table rows, per-row sum in slot order (pc_rows_segment_sum).
+extern "C" size_t pc_rows_index_grad_workspace_bytes(int64_t slots, int64_t n_rows) {
+  if (slots <= 0) return 0;
+  return align_up(size_t(slots) * 8, 256) + align_up(pc_sort_keys_workspace_bytes(slots), 256) +
+         align_up(size_t(n_rows + 1) * 8, 256) + align_up(size_t(slots) * 4, 256);
+}
+
+extern "C" int pc_rows_index_grad(const float* rows, const int64_t* index, int64_t slots, int64_t n_rows, int width, float* out,
+                                  void* workspace, size_t workspace_bytes, pc_stream_t stream) {
+  PC_REQUIRE(slots >= 0 && n_rows >= 0 && n_rows < (int64_t(1) << 31) && slots < (int64_t(1) << 31), PC_ERR_INVALID,
+             "rows_index_grad: bad sizes");
+  PC_REQUIRE(width > 0 && width % 4 == 0, PC_ERR_INVALID, "rows_index_grad: bad width=%d", width);
+  if (n_rows == 0) return PC_OK;
+  PC_REQUIRE(out, PC_ERR_INVALID, "rows_index_grad: null output");
+  cudaStream_t st = as_stream(stream);
+  if (slots == 0) {
+    PC_CUDA(cudaMemsetAsync(out, 0, size_t(n_rows) * width * sizeof(float), st));
+    return PC_OK;
+  }
+  PC_REQUIRE(rows && index && workspace, PC_ERR_INVALID, "rows_index_grad: null pointer");
+  PC_REQUIRE(workspace_bytes >= pc_rows_index_grad_workspace_bytes(slots, n_rows), PC_ERR_WORKSPACE, "rows_index_grad: workspace too small");
+  char* ws = reinterpret_cast<char*>(workspace);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(ws);          ws += align_up(size_t(slots) * 8, 256);
+  void* sort_ws = ws;                                         const size_t sort_bytes = pc_sort_keys_workspace_bytes(slots);
+  ws += align_up(sort_bytes, 256);
+  int64_t* rowptr = reinterpret_cast<int64_t*>(ws);           ws += align_up(size_t(n_rows + 1) * 8, 256);
+  int32_t* col = reinterpret_cast<int32_t*>(ws);
+  index_slot_keys_kernel<<<unsigned(ceil_div(slots, 256)), 256, 0, st>>>(index, slots, keys);
+  PC_LAUNCH_CHECK();
+  uint32_t mask = 0;
+  for (int b = 0; b < 4; ++b)
+    if ((uint64_t(n_rows > 1 ? n_rows - 1 : 1) >> (8 * b)) != 0) mask |= 1u << (4 + b);
+  if (int rc = pc_sort_keys(keys, slots, mask, sort_ws, sort_bytes, stream)) return rc;
+  if (int rc = pc_csr_from_sorted_keys(keys, slots, n_rows, rowptr, col, stream)) return rc;
+  return pc_rows_segment_sum(rows, rowptr, col, n_rows, width, out, stream);
 }

@@ -63,7 +63,16 @@ struct LinearParams {
   int epilogue;
   const float* aux; int ld_aux;      // EPI_TANH_GRAD: tanh output t (y = acc * (1 - t^2)); EPI_BIAS_SELECT: fallback rows
   const int64_t* rowptr;             // EPI_BIAS_SELECT: row keeps acc + bias iff rowptr[r+1] > rowptr[r]
+  // TOPK instantiation (pc_type_scores_topk): a CTA owns a CONTIGUOUS run of tiles (m-tile major), every epilogue thread
+  // keeps the best tk_k columns of its row over the run and flushes them to list (segment, set) of the row
+  int tk_k;                          // entries per list (<= TK_MAX)
+  int tk_lists;                      // lists per row = 2 * max segments
+  int64_t tiles_per_cta;
+  double* tk_s;                      // [m, tk_lists, tk_k]
+  int64_t* tk_i;                     // [m, tk_lists, tk_k], pre-set to -1
+  int store_out;                     // write the [m, n] matrix as well
 };
+constexpr int TK_MAX = 4;
 
 // w_hi = rn_tf32(w), w_lo = rn_tf32(w - w_hi): the weight operand is split once per call, not once per tile
 __global__ void split_tf32_kernel(const float4* __restrict__ w, int64_t n4, float4* __restrict__ hi, float4* __restrict__ lo) {
@@ -77,6 +86,7 @@ __global__ void split_tf32_kernel(const float4* __restrict__ w, int64_t n4, floa
   lo[i] = l;
 }
 
+template <bool TOPK>
 __global__ void __launch_bounds__(LIN_THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
                      const __grid_constant__ CUtensorMap map_wlo,
@@ -115,7 +125,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.n; i += LIN_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  if (!TOPK)
+    for (int i = threadIdx.x; i < p.n; i += LIN_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -126,15 +137,19 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   const int64_t m_tiles = (p.m + BM - 1) / BM;
-  const int64_t tiles = m_tiles * p.n_tiles;
+  const int64_t all_tiles = m_tiles * p.n_tiles;
   const int k_blocks = p.k / BK;
   const uint32_t b_tile_bytes = uint32_t(p.bn) * BK * 4;
+  // tile schedule: round-robin over the CTAs, or (TOPK) one contiguous run per CTA; every role walks the same sequence
+  const int64_t t_first = TOPK ? int64_t(blockIdx.x) * p.tiles_per_cta : int64_t(blockIdx.x);
+  const int64_t tiles = TOPK ? (t_first + p.tiles_per_cta < all_tiles ? t_first + p.tiles_per_cta : all_tiles) : all_tiles;
+  const int64_t t_step = TOPK ? 1 : int64_t(gridDim.x);
 
   if (warp == 0) {
     // ---------------- TMA producer, activations (HBM)
     if (lane == 0) {
       Ring<A_STAGES> ra;
-      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int64_t t = t_first; t < tiles; t += t_step) {
         const int m0 = int((t / p.n_tiles) * BM);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(a_empty + 8 * ra.stage, ra.phase ^ 1);
@@ -148,7 +163,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ---------------- TMA producer, pre-split weights (L2)
     if (lane == 0) {
       Ring<B_STAGES> rb;
-      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int64_t t = t_first; t < tiles; t += t_step) {
         const int n0 = int(t % p.n_tiles) * p.bn;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(b_empty + 8 * rb.stage, rb.phase ^ 1);
@@ -172,7 +187,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // a_hi . [W_hi | W_lo] is ONE 256-wide MMA (a_hi is fetched from shared memory once instead of twice)
     const bool wide = p.bn == MAX_BN;
     const uint32_t idesc_wide = instr_desc_tf32(2 * MAX_BN);
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    for (int64_t t = t_first; t < tiles; t += t_step) {
       mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_main = tmem_base + uint32_t(acc * 2 * MAX_BN), d_cross = d_main + MAX_BN;
@@ -220,7 +235,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     Ring<A_STAGES> ra;
     Ring<LO_STAGES> rl;
     const int tid = threadIdx.x - 256;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    for (int64_t t = t_first; t < tiles; t += t_step) {
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(a_full + 8 * ra.stage, ra.phase);
         mbar_wait(lo_empty + 8 * rl.stage, rl.phase ^ 1);
@@ -264,6 +279,28 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const bool aux_tile = p.epilogue == EPI_TANH_GRAD || p.epilogue == EPI_BIAS_ADD;
     const bool has_aux = aux_tile || p.epilogue == EPI_BIAS_SELECT;
     uint32_t aux_phase = 0;
+    // TOPK: best tk_k (score, column) of my row over this CTA's run of tiles; columns arrive ascending, so the strict
+    // comparison keeps the lower column on ties
+    float tk_v[TK_MAX];
+    int tk_c[TK_MAX];
+    int64_t tk_mtile = -1;
+    auto tk_reset = [&]() {
+#pragma unroll
+      for (int j = 0; j < TK_MAX; ++j) { tk_v[j] = -INFINITY; tk_c[j] = -1; }
+    };
+    auto tk_flush = [&]() {
+      if (!TOPK || tk_mtile < 0) return;
+      const int64_t frow = tk_mtile * BM + trow;
+      if (frow >= p.m) return;
+      const int64_t first_cta = (tk_mtile * p.n_tiles) / p.tiles_per_cta;      // CTA that holds the m-tile's first n-tile
+      const int64_t list = (int64_t(blockIdx.x) - first_cta) * 2 + set;
+      double* os = p.tk_s + (frow * p.tk_lists + list) * p.tk_k;
+      int64_t* oi = p.tk_i + (frow * p.tk_lists + list) * p.tk_k;
+#pragma unroll
+      for (int j = 0; j < TK_MAX; ++j)
+        if (j < p.tk_k) { os[j] = double(tk_v[j]); oi[j] = int64_t(tk_c[j]); }
+    };
+    if (TOPK) tk_reset();
     auto prefetch_aux = [&](int64_t tile) {
       if (!has_aux || tile >= tiles) return;
       const int64_t prow = (tile / p.n_tiles) * BM + trow;
@@ -272,12 +309,17 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                      "r"(uint32_t(p.bn) * 4u)
                      : "memory");
     };
-    prefetch_aux(blockIdx.x);
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    prefetch_aux(t_first);
+    for (int64_t t = t_first; t < tiles; t += t_step) {
       const int m0 = int((t / p.n_tiles) * BM);
       const int64_t row = int64_t(m0) + trow;
       const int n0 = int(t % p.n_tiles) * p.bn;
-      prefetch_aux(t + gridDim.x);
+      prefetch_aux(t + t_step);
+      if (TOPK && t / p.n_tiles != tk_mtile) {
+        tk_flush();
+        tk_reset();
+        tk_mtile = t / p.n_tiles;
+      }
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       bool keep = true;
@@ -295,13 +337,33 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         tmem_ld_wait32(rc);
         const int n = n0 + c0;
         float y[32];
+        if (TOPK) {
+          if (n >= p.n) continue;                     // chunk past the last column (n need not be a multiple of 128)
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = lds128(bias_addr + (n + j) * 4);
-          y[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]) + b4.x;
-          y[j + 1] = __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]) + b4.y;
-          y[j + 2] = __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]) + b4.z;
-          y[j + 3] = __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]) + b4.w;
+          for (int j = 0; j < 32; ++j) {
+            y[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+            if (n + j < p.n && y[j] > tk_v[TK_MAX - 1]) {      // unused tail entries of the list stay at -inf
+              float v = y[j];
+              int c = n + j;
+#pragma unroll
+              for (int q = 0; q < TK_MAX; ++q) {
+                if (v > tk_v[q]) {
+                  const float tv = tk_v[q]; const int tc = tk_c[q];
+                  tk_v[q] = v; tk_c[q] = c; v = tv; c = tc;
+                }
+              }
+            }
+          }
+          if (!p.store_out) continue;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = lds128(bias_addr + (n + j) * 4);
+            y[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]) + b4.x;
+            y[j + 1] = __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]) + b4.y;
+            y[j + 2] = __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]) + b4.z;
+            y[j + 3] = __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]) + b4.w;
+          }
         }
         if (p.epilogue == EPI_BIAS_TANH) {
 #pragma unroll
@@ -353,6 +415,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         acc_phase ^= 1;
       }
     }
+    tk_flush();
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
@@ -681,12 +744,89 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   }
   static bool configured[64] = {};
   if (first_use_on_device(configured))
-    PC_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    PC_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   const int64_t tiles = ((m + BM - 1) / BM) * p.n_tiles;
   const int grid = int(tiles < sm_count() ? tiles : sm_count());
-  linear_tf32x3_kernel<<<grid, LIN_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out0, map_out1, map_aux, p);
+  p.tk_k = 0; p.tk_lists = 0; p.tiles_per_cta = 0; p.tk_s = nullptr; p.tk_i = nullptr; p.store_out = 1;
+  linear_tf32x3_kernel<false><<<grid, LIN_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out0, map_out1, map_aux, p);
   PC_LAUNCH_CHECK();
   return PC_OK;
+}
+
+// ---------------------------------------------------------------- [B, L] x [T, L]^T scoring with the row top-k in the epilogue
+namespace {
+struct ScoreSchedule {
+  int64_t m_tiles, n_tiles, tiles, per;
+  int grid, max_segs;
+};
+ScoreSchedule score_schedule(int64_t m, int n) {
+  ScoreSchedule sc;
+  sc.m_tiles = (m + BM - 1) / BM;
+  sc.n_tiles = (n + MAX_BN - 1) / MAX_BN;
+  sc.tiles = sc.m_tiles * sc.n_tiles;
+  const int64_t sms = sm_count();
+  sc.per = (sc.tiles + sms - 1) / sms;
+  if (sc.per < 1) sc.per = 1;
+  sc.grid = int((sc.tiles + sc.per - 1) / sc.per);
+  sc.max_segs = int((sc.n_tiles - 1) / sc.per + 2);      // CTAs whose runs can intersect one m-tile's n-tiles
+  return sc;
+}
+}  // namespace
+
+extern "C" size_t pc_type_scores_topk_workspace_bytes(int64_t m, int n, int k, int topk) {
+  if (m <= 0 || n <= 0 || k <= 0 || topk <= 0) return 0;
+  const ScoreSchedule sc = score_schedule(m, n);
+  return 2 * align_up(size_t(n) * k * sizeof(float), 256) + size_t(m) * size_t(2 * sc.max_segs) * size_t(topk) * 16;
+}
+
+extern "C" int pc_type_scores_topk(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, float* out,
+                                   int64_t ld_out, int topk, double* out_scores, int64_t* out_idx, void* workspace,
+                                   size_t workspace_bytes, pc_stream_t stream) {
+  PC_REQUIRE(m >= 0, PC_ERR_INVALID, "type_scores_topk: negative row count");
+  if (m == 0) return PC_OK;
+  PC_REQUIRE(a && w && out_scores && out_idx && workspace, PC_ERR_INVALID, "type_scores_topk: null pointer");
+  PC_REQUIRE(k >= BK && k % BK == 0 && k <= 4096, PC_ERR_UNSUPPORTED, "type_scores_topk: k=%d must be a multiple of %d", k, BK);
+  PC_REQUIRE(n >= 1 && n < (1 << 30), PC_ERR_UNSUPPORTED, "type_scores_topk: bad n=%d", n);
+  PC_REQUIRE(topk >= 1 && topk <= TK_MAX && topk <= n, PC_ERR_UNSUPPORTED, "type_scores_topk: topk=%d outside [1,%d] (or > n)", topk, TK_MAX);
+  PC_REQUIRE(lda % 4 == 0 && reinterpret_cast<uintptr_t>(a) % 16 == 0, PC_ERR_INVALID, "type_scores_topk: A must be 16-byte aligned, lda % 4 == 0");
+  PC_REQUIRE(!out || (ld_out % 4 == 0 && ld_out >= n && reinterpret_cast<uintptr_t>(out) % 16 == 0), PC_ERR_INVALID,
+             "type_scores_topk: out must be 16-byte aligned with ld_out % 4 == 0 (TMA)");
+  PC_REQUIRE(workspace_bytes >= pc_type_scores_topk_workspace_bytes(m, n, k, topk), PC_ERR_WORKSPACE, "type_scores_topk: workspace too small");
+  const ScoreSchedule sc = score_schedule(m, n);
+  LinearParams p;
+  p.m = m; p.n = n; p.k = k; p.bn = MAX_BN; p.n_tiles = int(sc.n_tiles);
+  p.bias = nullptr; p.out0 = out; p.ld0 = int(ld_out); p.split = n; p.out1 = nullptr; p.ld1 = 0;
+  p.epilogue = EPI_BIAS; p.aux = nullptr; p.ld_aux = 0; p.rowptr = nullptr;
+  p.tk_k = topk; p.tk_lists = 2 * sc.max_segs; p.tiles_per_cta = sc.per; p.store_out = out ? 1 : 0;
+  cudaStream_t st = as_stream(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  const size_t wbytes = align_up(size_t(n) * k * sizeof(float), 256);
+  float* w_hi = reinterpret_cast<float*>(ws);
+  float* w_lo = reinterpret_cast<float*>(ws + wbytes);
+  const size_t entries = size_t(m) * p.tk_lists * topk;
+  p.tk_s = reinterpret_cast<double*>(ws + 2 * wbytes);
+  p.tk_i = reinterpret_cast<int64_t*>(p.tk_s + entries);
+  PC_REQUIRE((int64_t(n) * k) % 4 == 0, PC_ERR_UNSUPPORTED, "type_scores_topk: n * k must be a multiple of 4");
+  const int64_t n4 = int64_t(n) * k / 4;
+  split_tf32_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(w), n4,
+                                                               reinterpret_cast<float4*>(w_hi), reinterpret_cast<float4*>(w_lo));
+  PC_LAUNCH_CHECK();
+  PC_CUDA(cudaMemsetAsync(p.tk_i, 0xFF, entries * sizeof(int64_t), st));      // -1 = empty slot (lists a CTA never visits)
+  CUtensorMap map_a, map_whi, map_wlo, map_out;
+  if (int rc = make_map(&map_a, a, m, k, lda, BM, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return rc;
+  if (int rc = make_map(&map_whi, w_hi, n, k, k, MAX_BN)) return rc;
+  if (int rc = make_map(&map_wlo, w_lo, n, k, k, MAX_BN)) return rc;
+  if (out) {
+    if (int rc = make_map(&map_out, out, m, n, ld_out, BM)) return rc;
+  } else {
+    map_out = map_a;
+  }
+  static bool configured[64] = {};
+  if (first_use_on_device(configured))
+    PC_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  linear_tf32x3_kernel<true><<<sc.grid, LIN_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out, map_out, map_out, p);
+  PC_LAUNCH_CHECK();
+  return pc_topk_merge(p.tk_s, p.tk_i, m, p.tk_lists, topk, out_scores, out_idx, stream);
 }
 
 // row-major fp32 [rows, cols] viewed as [cols/32 groups][rows][32]: boxes of [groups, 16 rows, 32 cols]

@@ -41,6 +41,103 @@ def _allreduce_sums(sums: torch.Tensor, count: int, group, sync: bool, total: Op
     return sums, count
 
 
+def ffn_forward_core(x, w0, b0, gamma, beta, w3, b3, w5, b5, training, eps, momentum, run_mean, run_var, num_batches,
+                     group=None, sync_bn=False, total=None):
+    """Linear -> BatchNorm1d -> Tanh -> Linear -> Tanh -> Linear (product2vec.py:14-21) on [rows, 128] with the C-ABI kernels:
+    tcgen05 projections (tanh in the epilogue), float64 fixed-order column statistics, one BN-apply + tanh pass.
+    Returns (z1, a1, a2, h, mean, rstd, count); running statistics are updated in place with nn.BatchNorm1d's rule
+    (momentum None = cumulative average over num_batches_tracked, unbiased variance)."""
+    n = x.shape[0]
+    z1 = ops.linear_tc(x, w0, b0)
+    if training or run_mean is None:
+        sums, count = _allreduce_sums(ops.col_stats(z1), n, group, sync_bn, total)
+        if training and count <= 1:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(z1.shape)}")
+        mean64 = sums[0] / count
+        var64 = (sums[1] / count - mean64 * mean64).clamp_(min=0.0)
+        if training and run_mean is not None:
+            with torch.no_grad():
+                m_ = momentum if momentum is not None else 1.0 / max(int(num_batches) if num_batches is not None else 1, 1)
+                run_mean.mul_(1 - m_).add_(mean64.to(F32), alpha=m_)
+                run_var.mul_(1 - m_).add_((var64 * (count / max(count - 1, 1))).to(F32), alpha=m_)
+    else:
+        count = n
+        mean64, var64 = run_mean.double(), run_var.double()
+    rstd64 = torch.rsqrt(var64 + eps)
+    mean, rstd = mean64.to(F32), rstd64.to(F32)
+    scale = (gamma.double() * rstd64).to(F32)
+    shift = (beta.double() - mean64 * gamma.double() * rstd64).to(F32)
+    a1 = ops.scale_shift_tanh(z1, scale, shift, tanh=True)
+    a2 = ops.linear_tc(a1, w3, b3, ops.EPI_BIAS_TANH)
+    h = ops.linear_tc(a2, w5, b5)
+    return z1, a1, a2, h, mean, rstd, count
+
+
+def ffn_backward_core(d_h, x, z1, a1, a2, mean, rstd, gamma, w0, w3, w5, batch_stats, count, group=None, sync_bn=False,
+                      need_dx=True):
+    """Backward of ffn_forward_core: tanh' lives in the GEMM epilogues, the BatchNorm input gradient is one reduction
+    + one pass with folded coefficients.  `batch_stats`: the forward normalised with the statistics of its own rows."""
+    dw5, db5 = ops.wgrad_tc(d_h, a2)
+    d_p2 = ops.linear_tc(d_h, w5.t().contiguous(), None, ops.EPI_TANH_GRAD, aux=a2)
+    dw3, db3 = ops.wgrad_tc(d_p2, a1)
+    d_y = ops.linear_tc(d_p2, w3.t().contiguous(), None, ops.EPI_TANH_GRAD, aux=a1)
+    sums = ops.bn_bwd_reduce(d_y, z1, mean, rstd)
+    world = 1
+    if batch_stats:
+        sums, _ = _allreduce_sums(sums, 0, group, sync_bn, count)
+        if sync_bn and dist.is_initialized():
+            world = dist.get_world_size(group)
+    d_beta64, d_gamma64 = sums[0], sums[1]
+    g64, r64, m64 = gamma.double(), rstd.double(), mean.double()
+    if batch_stats:
+        ca = g64 * r64
+        cb = -(g64 * r64 * r64 * d_gamma64 / count)
+        cc = -cb * m64 - g64 * r64 * d_beta64 / count
+        d_z1 = ops.affine2(d_y, z1, ca.to(F32), cb.to(F32), cc.to(F32))
+    else:
+        d_z1 = ops.scale_shift_tanh(d_y, (g64 * r64).to(F32), torch.zeros_like(mean), tanh=False)
+    dw0, db0 = ops.wgrad_tc(d_z1, x)
+    dx = ops.linear_tc(d_z1, w0.t().contiguous(), None) if need_dx else None
+    # gamma / beta gradients are already global sums under SyncBN; the caller's gradient all-reduce sums over ranks
+    d_gamma = (d_gamma64 / world).to(F32)
+    d_beta = (d_beta64 / world).to(F32)
+    return dx, dw0, db0, d_gamma, d_beta, dw3, db3, dw5, db5
+
+
+class _FFNRows(torch.autograd.Function):
+    """The FFN on any batch of rows as one autograd node (the drop-in forward(features, neighbors) path:
+    get_initial_embedding, product2vec.py:31-46) - no ATen arithmetic on row-sized tensors."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, gamma, beta, w3, b3, w5, b5, cfg):
+        x = x.contiguous()
+        z1, a1, a2, h, mean, rstd, count = ffn_forward_core(
+            x, w0, b0, gamma, beta, w3, b3, w5, b5, cfg["training"], cfg["eps"], cfg["momentum"], cfg["running_mean"],
+            cfg["running_var"], cfg.get("num_batches_tracked"))
+        ctx.save_for_backward(x, z1, a1, a2, mean, rstd, gamma, w0, w3, w5)
+        ctx.batch_stats = cfg["training"] or cfg["running_mean"] is None
+        ctx.count = count
+        return h
+
+    @staticmethod
+    def backward(ctx, d_h):
+        x, z1, a1, a2, mean, rstd, gamma, w0, w3, w5 = ctx.saved_tensors
+        grads = ffn_backward_core(d_h.contiguous(), x, z1, a1, a2, mean, rstd, gamma, w0, w3, w5, ctx.batch_stats, ctx.count,
+                                  need_dx=ctx.needs_input_grad[0])
+        return (*grads, None)
+
+
+def ffn_rows(ffn, rows: torch.Tensor, training: bool) -> torch.Tensor:
+    """ffn(rows) through _FFNRows for an nn.Sequential laid out as product2vec.py:14-21."""
+    l0, bn, _, l3, _, l5 = ffn
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    cfg = dict(training=training or not bn.track_running_stats, eps=bn.eps, momentum=bn.momentum, running_mean=bn.running_mean,
+               running_var=bn.running_var,
+               num_batches_tracked=int(bn.num_batches_tracked) if (bn.momentum is None and bn.num_batches_tracked is not None) else None)
+    return _FFNRows.apply(rows, l0.weight, l0.bias, bn.weight, bn.bias, l3.weight, l3.bias, l5.weight, l5.bias, cfg)
+
+
 class _P2VGraphLayer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w0, b0, gamma, beta, w3, b3, w5, b5, w_in, b_in, w_o, b_o, cfg):
@@ -51,27 +148,9 @@ class _P2VGraphLayer(torch.autograd.Function):
         run_mean, run_var = cfg["running_mean"], cfg["running_var"]     # buffers: updated in place, never differentiated
         x = x.contiguous()
         n = x.shape[0]
-        z1 = ops.linear_tc(x, w0, b0)
-        if training:
-            total = plan.bounds[-1] - plan.bounds[0] if plan is not None else None
-            sums, count = _allreduce_sums(ops.col_stats(z1), n, group, sync_bn, total)
-            mean64 = sums[0] / count
-            var64 = (sums[1] / count - mean64 * mean64).clamp_(min=0.0)
-            if run_mean is not None:
-                with torch.no_grad():
-                    m_ = 0.1 if momentum is None else momentum
-                    run_mean.mul_(1 - m_).add_(mean64.to(F32), alpha=m_)
-                    run_var.mul_(1 - m_).add_((var64 * (count / max(count - 1, 1))).to(F32), alpha=m_)
-        else:
-            count = n
-            mean64, var64 = run_mean.double(), run_var.double()
-        rstd64 = torch.rsqrt(var64 + eps)
-        mean, rstd = mean64.to(F32), rstd64.to(F32)
-        scale = (gamma.double() * rstd64).to(F32)
-        shift = (beta.double() - mean64 * gamma.double() * rstd64).to(F32)
-        a1 = ops.scale_shift_tanh(z1, scale, shift, tanh=True)
-        a2 = ops.linear_tc(a1, w3, b3, ops.EPI_BIAS_TANH)
-        h = ops.linear_tc(a2, w5, b5)
+        total = plan.bounds[-1] - plan.bounds[0] if plan is not None else None
+        z1, a1, a2, h, mean, rstd, count = ffn_forward_core(x, w0, b0, gamma, beta, w3, b3, w5, b5, training, eps, momentum,
+                                                            run_mean, run_var, cfg.get("num_batches_tracked"), group, sync_bn, total)
         qg = torch.empty(n, 256, dtype=F32, device=x.device)
         n_ext = graph.n_cols
         peer = plan.peer if plan is not None else None
@@ -150,31 +229,8 @@ class _P2VGraphLayer(torch.autograd.Function):
             dw_kv, db_kv = ops.wgrad_tc(dkv[:n], h)
             dw_in, db_in = torch.cat([dw_q, dw_kv]), torch.cat([db_q, db_kv])
             d_h = ops.linear_tc(dkv[:n], w_in_t[:, 128:].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_h)
-        # FFN
-        dw5, db5 = ops.wgrad_tc(d_h, a2)
-        d_p2 = ops.linear_tc(d_h, w5.t().contiguous(), None, ops.EPI_TANH_GRAD, aux=a2)
-        dw3, db3 = ops.wgrad_tc(d_p2, a1)
-        d_y = ops.linear_tc(d_p2, w3.t().contiguous(), None, ops.EPI_TANH_GRAD, aux=a1)
-        sums = ops.bn_bwd_reduce(d_y, z1, mean, rstd)
-        world = 1
-        if training:
-            sums, _ = _allreduce_sums(sums, 0, group, sync_bn, count)
-            if sync_bn and dist.is_initialized():
-                world = dist.get_world_size(group)
-        d_beta64, d_gamma64 = sums[0], sums[1]
-        g64, r64, m64 = gamma.double(), rstd.double(), mean.double()
-        if training:
-            ca = g64 * r64
-            cb = -(g64 * r64 * r64 * d_gamma64 / count)
-            cc = -cb * m64 - g64 * r64 * d_beta64 / count
-            d_z1 = ops.affine2(d_y, z1, ca.to(F32), cb.to(F32), cc.to(F32))
-        else:
-            d_z1 = ops.scale_shift_tanh(d_y, (g64 * r64).to(F32), torch.zeros_like(mean), tanh=False)
-        dw0, db0 = ops.wgrad_tc(d_z1, x)
-        dx = ops.linear_tc(d_z1, w0.t().contiguous(), None) if ctx.needs_input_grad[0] else None
-        # gamma / beta gradients are already global sums under SyncBN; the caller's gradient all-reduce sums over ranks
-        d_gamma = (d_gamma64 / world).to(F32)
-        d_beta = (d_beta64 / world).to(F32)
+        dx, dw0, db0, d_gamma, d_beta, dw3, db3, dw5, db5 = ffn_backward_core(
+            d_h, x, z1, a1, a2, mean, rstd, gamma, w0, w3, w5, training, count, group, sync_bn, ctx.needs_input_grad[0])
         return (dx, dw0, db0, d_gamma, d_beta, dw3, db3, dw5, db5, dw_in, db_in, dw_o, db_o, None)
 
 
@@ -186,12 +242,18 @@ def p2v_graph_layer(model, x: torch.Tensor, graph: ops.CSRGraph, plan=None, grou
     if model.training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     cfg = dict(graph=graph, plan=plan, heads=model.heads, dropout_p=p_drop, seed=seed, training=model.training, eps=bn.eps,
-               momentum=bn.momentum, group=group, sync_bn=sync_bn, running_mean=bn.running_mean, running_var=bn.running_var)
+               momentum=bn.momentum, group=group, sync_bn=sync_bn, running_mean=bn.running_mean, running_var=bn.running_var,
+               num_batches_tracked=int(bn.num_batches_tracked) if (bn.momentum is None and bn.num_batches_tracked is not None) else None)
     return _P2VGraphLayer.apply(x, l0.weight, l0.bias, bn.weight, bn.bias, l3.weight, l3.bias, l5.weight, l5.bias,
                                 att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias, cfg)
 
 
-def fused_supported(model, x: torch.Tensor) -> bool:
-    l0, bn, _, l3, _, l5 = model.ffn
+def ffn_supported(ffn, x: torch.Tensor) -> bool:
+    """Shapes the tcgen05 kernels are instantiated for (the reference's default config, config.py:8-12)."""
+    l0, bn, _, l3, _, l5 = ffn
     return (x.is_cuda and x.dtype == F32 and x.dim() == 2 and l0.in_features == 128 and l0.out_features == 256
             and l3.out_features == 256 and l5.out_features == 128 and bn.affine and bn.track_running_stats)
+
+
+def fused_supported(model, x: torch.Tensor) -> bool:
+    return ffn_supported(model.ffn, x)

@@ -352,6 +352,43 @@ class _HingeRows(torch.autograd.Function):
         return da, dp, dn, None, None, None, None
 
 
+def index_rows_grad(rows: torch.Tensor, index: torch.Tensor, n_rows: int) -> torch.Tensor:
+    """Dense [n_rows, W] gradient of table[index] from the gradient rows [S, W], no float atomics (pc_rows_index_grad:
+    slots sorted stably by table row, summed per row in slot order)."""
+    rows = rows.contiguous()
+    index = index.reshape(-1).to(I64).contiguous()
+    slots, w = rows.shape
+    out = torch.empty(n_rows, w, dtype=F32, device=rows.device)
+    ws = _lib.workspace(_lib.LIB.pc_rows_index_grad_workspace_bytes(slots, n_rows), rows.device)
+    call("pc_rows_index_grad", dev(rows, F32, "rows"), dev(index, I64, "index"), slots, n_rows, w, dev(out, F32, "out"),
+         dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return out
+
+
+class _GatherRows(torch.autograd.Function):
+    """table[index] (nn.Embedding / advanced-index gather, p_companion.py:49,54,66) with a deterministic dense gradient."""
+
+    @staticmethod
+    def forward(ctx, table, index):
+        table = table.contiguous()
+        index = index.reshape(-1).to(I64).contiguous()
+        ctx.save_for_backward(index)
+        ctx.n_rows = table.shape[0]
+        return rows_gather(table, index)
+
+    @staticmethod
+    def backward(ctx, d_rows):
+        (index,) = ctx.saved_tensors
+        return index_rows_grad(d_rows, index, ctx.n_rows), None
+
+
+def gather_rows(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """[len(index), W] rows of `table` (differentiable with respect to the table when it requires grad)."""
+    if table.requires_grad and torch.is_grad_enabled():
+        return _GatherRows.apply(table, index)
+    return rows_gather(table.detach().contiguous(), index.reshape(-1).to(I64).contiguous())
+
+
 class _TripletFromTable(torch.autograd.Function):
     """Triplet hinge on rows of one embedding table selected by index (anchors | positives | negatives).
     Backward returns a dense d_table built without float atomics: the slot list is stably sorted by node
@@ -382,14 +419,7 @@ class _TripletFromTable(torch.autograd.Function):
         call("pc_hinge_rows_bwd", dev(a, F32, "a"), dev(p, F32, "p"), dev(n, F32, "n"), batch, 1, kneg, d, margin, eps,
              dev(g, F32, "grad"), dev(grads[:batch], F32, "da"), dev(grads[batch: 2 * batch], F32, "dp"),
              dev(grads[2 * batch:], F32, "dn"), stream())
-        slots = rows.shape[0]
-        keys = pack_keys(slot_nodes.to(I32), torch.arange(slots, dtype=I32, device=rows.device))
-        node_bytes = max(1, ((max(n_nodes, 2) - 1).bit_length() + 7) // 8)
-        sort_keys_(keys, ((1 << node_bytes) - 1) << 4)             # stable: slots stay ascending inside a node
-        rowptr, col = csr_from_sorted_keys(keys, n_nodes)
-        d_table = torch.empty(n_nodes, d, dtype=F32, device=rows.device)
-        call("pc_rows_segment_sum", dev(grads, F32, "rows"), dev(rowptr, I64, "rowptr"), dev(col, I32, "col"), n_nodes, d,
-             dev(d_table, F32, "out"), stream())
+        d_table = index_rows_grad(grads, slot_nodes, n_nodes)
         return d_table, None, None, None, None, None
 
 
@@ -463,21 +493,15 @@ class _HingeTypeFactored(torch.autograd.Function):
     def backward(ctx, g):
         base, weight, per, pos, neg = ctx.saved_tensors
         rows, nt = base.shape[0], weight.shape[0]
-        coef = torch.where((per > 0) & (pos != neg), g.to(F32) / rows, torch.zeros((), dtype=F32, device=per.device))
-        d_base = d_w = None
-        if ctx.needs_input_grad[0]:
-            d_base = coef.unsqueeze(1) * (weight[neg] - weight[pos])
-        if ctx.needs_input_grad[1]:
-            contrib = coef.unsqueeze(1) * base                                   # [B, L]
-            vals = torch.cat([-contrib, contrib]).contiguous()                   # slot i: pos_i, slot B + i: neg_i
-            slots = 2 * rows
-            keys = pack_keys(torch.cat([pos, neg]).to(I32), torch.arange(slots, dtype=I32, device=base.device))
-            type_bytes = max(1, ((max(nt, 2) - 1).bit_length() + 7) // 8)
-            sort_keys_(keys, ((1 << type_bytes) - 1) << 4)                       # stable: slots stay ascending inside a type
-            rowptr, col = csr_from_sorted_keys(keys, nt)
-            d_w = torch.empty(nt, base.shape[1], dtype=F32, device=base.device)
-            call("pc_rows_segment_sum", dev(vals, F32, "rows"), dev(rowptr, I64, "rowptr"), dev(col, I32, "col"), nt,
-                 base.shape[1], dev(d_w, F32, "out"), stream())
+        need_b, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g = g.contiguous().to(F32)
+        base_c, weight_c = base.contiguous(), weight.contiguous()
+        d_base = torch.empty_like(base_c) if need_b else None
+        vals = torch.empty(2 * rows, base.shape[1], dtype=F32, device=base.device) if need_w else None   # slot i: pos_i, B + i: neg_i
+        call("pc_hinge_type_factored_bwd", dev(per, F32, "per"), dev(pos, I64, "pos"), dev(neg, I64, "neg"), dev(g, F32, "grad"),
+             dev(base_c, F32, "base"), dev(weight_c, F32, "weight"), rows, base.shape[1], dev(d_base, F32, "d_base"),
+             dev(vals, F32, "vals"), stream())
+        d_w = index_rows_grad(vals, torch.cat([pos, neg]), nt) if need_w else None
         return d_base, d_w, None, None, None, None
 
 
@@ -488,6 +512,113 @@ def type_hinge(sims, pos, neg, margin: float) -> torch.Tensor:
     if factors is not None and factors[0].shape[0] == sims.shape[0] and factors[1].shape[0] == sims.shape[1]:
         return _HingeTypeFactored.apply(factors[0], factors[1], sims.detach(), pos, neg, float(margin))
     return _HingeType.apply(sims, pos, neg, float(margin))
+
+
+# --------------------------------------------------------------------------- P-Companion small layers
+class _MLP2(torch.autograd.Function):
+    """W2 . dropout(relu(W1 . x + b1)) + b2 on x = table[index] (or the rows of `table` when index is None):
+    type_transition.py:15-20 (+ the nn.Embedding gather of p_companion.py:54) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, table, index, w1, b1, w2, b2, p_drop: float, seed: int):
+        table = table.contiguous()
+        idx = None if index is None else index.reshape(-1).to(I64).contiguous()
+        rows = table.shape[0] if idx is None else idx.numel()
+        hid, d_in = w1.shape
+        d_out = w2.shape[0]
+        hidden = torch.empty(rows, hid, dtype=F32, device=table.device)
+        out = torch.empty(rows, d_out, dtype=F32, device=table.device)
+        w1c, w2c = w1.contiguous(), w2.contiguous()
+        call("pc_mlp2_fwd", dev(table, F32, "table"), dev(idx, I64, "index"), rows, d_in, hid, d_out, dev(w1c, F32, "w1"),
+             dev(b1, F32, "b1"), dev(w2c, F32, "w2"), dev(b2, F32, "b2"), float(p_drop), int(seed), dev(hidden, F32, "hidden"),
+             dev(out, F32, "out"), stream())
+        ctx.save_for_backward(table, idx, hidden, w1c, w2c)
+        ctx.p_drop = float(p_drop)
+        ctx.has_bias = (b1 is not None, b2 is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        table, idx, hidden, w1, w2 = ctx.saved_tensors
+        d_out = d_out.contiguous()
+        rows = d_out.shape[0]
+        hid, d_in = w1.shape
+        n_out = w2.shape[0]
+        need_x = ctx.needs_input_grad[0]
+        d_x = torch.empty(rows, d_in, dtype=F32, device=d_out.device) if need_x else None
+        d_w1, d_w2 = torch.empty_like(w1), torch.empty_like(w2)
+        d_b1 = torch.empty(hid, dtype=F32, device=d_out.device) if ctx.has_bias[0] else None
+        d_b2 = torch.empty(n_out, dtype=F32, device=d_out.device) if ctx.has_bias[1] else None
+        if rows == 0:
+            return (torch.zeros_like(table) if need_x else None, None, torch.zeros_like(w1), None if d_b1 is None else d_b1.zero_(),
+                    torch.zeros_like(w2), None if d_b2 is None else d_b2.zero_(), None, None)
+        ws = _lib.workspace(_lib.LIB.pc_mlp2_bwd_workspace_bytes(d_in, hid, n_out), d_out.device)
+        call("pc_mlp2_bwd", dev(d_out, F32, "d_out"), dev(table, F32, "table"), dev(idx, I64, "index"), dev(hidden, F32, "hidden"),
+             rows, d_in, hid, n_out, dev(w1, F32, "w1"), dev(w2, F32, "w2"), ctx.p_drop, dev(d_x, F32, "d_x"), dev(d_w1, F32, "d_w1"),
+             dev(d_b1, F32, "d_b1"), dev(d_w2, F32, "d_w2"), dev(d_b2, F32, "d_b2"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+        d_table = None
+        if need_x:
+            d_table = d_x if idx is None else index_rows_grad(d_x, idx, table.shape[0])
+        return d_table, None, d_w1, d_b1, d_w2, d_b2, None, None
+
+
+def mlp2_supported(d_in: int, hid: int, d_out: int) -> bool:
+    return 4 <= d_in <= 256 and 1 <= hid <= 128 and 1 <= d_out <= 256
+
+
+def mlp2(table: torch.Tensor, index: Optional[torch.Tensor], w1, b1, w2, b2, p_drop: float = 0.0, seed: int = 0) -> torch.Tensor:
+    if not table.is_cuda:
+        raise RuntimeError(f"pcompanion_b200.ops.mlp2: input on {table.device}; CUDA only (no CPU fallback)")
+    return _MLP2.apply(table, index, w1, b1, w2, b2, float(p_drop), int(seed))
+
+
+class _ItemCombine(torch.autograd.Function):
+    """pi[:, None, :] * tp.view(B, Kt, D)   (item_prediction.py:38)."""
+
+    @staticmethod
+    def forward(ctx, pi, tp, kt: int):
+        pi, tp = pi.contiguous(), tp.contiguous()
+        b, d = pi.shape
+        out = torch.empty(b, kt, d, dtype=F32, device=pi.device)
+        call("pc_item_combine_fwd", dev(pi, F32, "pi"), dev(tp, F32, "tp"), b, kt, d, dev(out, F32, "out"), stream())
+        ctx.save_for_backward(pi, tp)
+        ctx.kt = kt
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        pi, tp = ctx.saved_tensors
+        d_out = d_out.contiguous()
+        d_pi, d_tp = torch.empty_like(pi), torch.empty_like(tp)
+        call("pc_item_combine_bwd", dev(d_out, F32, "d_out"), dev(pi, F32, "pi"), dev(tp, F32, "tp"), pi.shape[0], ctx.kt,
+             pi.shape[1], dev(d_pi, F32, "d_pi"), dev(d_tp, F32, "d_tp"), stream())
+        return d_pi, d_tp, None
+
+
+def item_combine(pi: torch.Tensor, tp: torch.Tensor, kt: int) -> torch.Tensor:
+    if tp.shape[0] != pi.shape[0] * kt or tp.shape[1] != pi.shape[1]:
+        raise ValueError(f"item_combine: pi {tuple(pi.shape)} and tp {tuple(tp.shape)} do not match kt={kt}")
+    return _ItemCombine.apply(pi, tp, int(kt))
+
+
+def type_scores_topk_supported(base: torch.Tensor, weight: torch.Tensor, k: int) -> bool:
+    return (base.is_cuda and base.dtype == F32 and base.dim() == 2 and base.shape[1] % 32 == 0 and 32 <= base.shape[1] <= 4096
+            and weight.shape[0] % 4 == 0 and 1 <= k <= 4 and k <= weight.shape[0] and base.shape[0] > 0)
+
+
+def type_scores_topk(base: torch.Tensor, weight: torch.Tensor, k: int, materialize: bool = True):
+    """(S = base . W^T [B, T] or None, top scores f64 [B, k], top columns i64 [B, k]) - one tcgen05 GEMM whose epilogue keeps
+    the row top-k (pc_type_scores_topk; p_companion.py:60-64).  Not differentiable here: see dense.type_scores."""
+    base, weight = base.contiguous(), weight.contiguous()
+    b, l = base.shape
+    t = weight.shape[0]
+    sims = torch.empty(b, t, dtype=F32, device=base.device) if materialize else None
+    out_s = torch.empty(b, k, dtype=F64, device=base.device)
+    out_i = torch.empty(b, k, dtype=I64, device=base.device)
+    ws = _lib.workspace(_lib.LIB.pc_type_scores_topk_workspace_bytes(b, t, l, k), base.device)
+    call("pc_type_scores_topk", dev(base, F32, "base"), b, l, l, dev(weight, F32, "weight"), t, dev(sims, F32, "sims"), t, k,
+         dev(out_s, F64, "out_scores"), dev(out_i, I64, "out_idx"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return sims, out_s, out_i
 
 
 # --------------------------------------------------------------------------- retrieval

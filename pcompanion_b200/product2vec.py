@@ -119,6 +119,16 @@ class Product2Vec(nn.Module):
             return p2v_graph_layer(self, x, graph)          # one autograd node, every row-sized op in a C-ABI kernel
         h = self._ffn_rows(x)
         hq = self._ffn_rows(h) if double_ffn_query else h
+        if not torch.is_grad_enabled() and fused_supported(self, x):
+            # inference (generate_all_embeddings): raw kernels, the "rows without neighbours keep ffn(x)" select in the
+            # out-projection's epilogue
+            w, b = self.attention.in_proj_weight, self.attention.in_proj_bias
+            q = ops.linear_tc(hq, w[:128].contiguous(), b[:128].contiguous())
+            kv = ops.linear_tc(h, w[128:].contiguous(), b[128:].contiguous())
+            p, seed = self._dropout_args()
+            o, _ = ops.gat_fwd_raw(q, kv, graph, self.heads, p, seed)
+            return ops.linear_tc(o, self.attention.out_proj.weight.contiguous(), self.attention.out_proj.bias,
+                                 ops.EPI_BIAS_SELECT, aux=h, rowptr=graph.rowptr)
         out = self._attend(hq, h, graph)
         has_nbr = (graph.rowptr[1:] > graph.rowptr[:-1]).unsqueeze(1)
         return torch.where(has_nbr, out, h)
