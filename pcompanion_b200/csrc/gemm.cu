@@ -345,11 +345,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             if (n + j < p.n && y[j] > tk_v[TK_MAX - 1]) {      // unused tail entries of the list stay at -inf
               float v = y[j];
               int c = n + j;
-#pragma unroll
+              bool placed = false;                     // once placed, the displaced entries shift down unconditionally
+#pragma unroll                                         // (a strict comparison there would reorder equal scores)
               for (int q = 0; q < TK_MAX; ++q) {
-                if (v > tk_v[q]) {
+                if (placed || v > tk_v[q]) {
                   const float tv = tk_v[q]; const int tc = tk_c[q];
                   tk_v[q] = v; tk_c[q] = c; v = tv; c = tc;
+                  placed = true;
                 }
               }
             }

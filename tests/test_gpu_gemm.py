@@ -103,22 +103,58 @@ def test_wgrad_strided_operands():
 
 
 def test_linear_autograd_function_matches_torch_autograd():
+    """nn.Linear drop-in on the tcgen05 kernels (forward, dgrad, wgrad): the shapes of the Product2Vec projections and of
+    P-Companion's type projection (64 -> 128) / item projection (128 -> 128)."""
     from pcompanion_b200 import dense
     g = torch.Generator(device=dev()).manual_seed(3)
-    x = torch.randn(513, 128, generator=g, device=dev(), requires_grad=True)
-    w = (torch.randn(256, 128, generator=g, device=dev()) * 0.1).requires_grad_(True)
-    b = torch.randn(256, generator=g, device=dev(), requires_grad=True)
-    up = torch.randn(513, 256, generator=g, device=dev())
-    for tanh in (False, True):
-        for t in (x, w, b):
-            t.grad = None
-        (dense.linear(x, w, b, tanh=tanh) * up).sum().backward()
-        got = [t.grad.clone() for t in (x, w, b)]
+    for m, k, n in ((513, 128, 256), (768, 64, 128), (77, 128, 128)):
+        x = torch.randn(m, k, generator=g, device=dev(), requires_grad=True)
+        w = (torch.randn(n, k, generator=g, device=dev()) * 0.1).requires_grad_(True)
+        b = torch.randn(n, generator=g, device=dev(), requires_grad=True)
+        up = torch.randn(m, n, generator=g, device=dev())
+        out = dense.linear(x, w, b)
+        assert isinstance(out.grad_fn, dense._LinearTC._backward_cls)
+        (out * up).sum().backward()
         x64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
-        y = torch.nn.functional.linear(x64, w64, b64)
-        ((torch.tanh(y) if tanh else y) * up.double()).sum().backward()
-        for a, r, nm in zip(got, (x64, w64, b64), ("dx", "dw", "db")):
-            close(a, r.grad.cpu().numpy(), what=f"{nm} tanh={tanh}")
+        (torch.nn.functional.linear(x64, w64, b64) * up.double()).sum().backward()
+        for a, r, nm in zip((x, w, b), (x64, w64, b64), ("dx", "dw", "db")):
+            close(a.grad, r.grad.cpu().numpy(), what=f"{nm} {m}x{k}->{n}")
+
+
+def test_ffn_rows_node_matches_torch_autograd_with_batchnorm():
+    """The drop-in path's FFN as one native autograd node (Linear -> BatchNorm1d -> tanh -> Linear -> tanh -> Linear,
+    product2vec.py:14-21): output, every gradient and the running statistics against float64 nn modules; momentum=None
+    (cumulative average) and the single-row error of nn.BatchNorm1d."""
+    import torch.nn as nn
+    from pcompanion_b200 import dense
+    g = torch.Generator(device=dev()).manual_seed(8)
+    for momentum in (0.1, None):
+        torch.manual_seed(0)
+        ffn = nn.Sequential(nn.Linear(128, 256), nn.BatchNorm1d(256, momentum=momentum), nn.Tanh(), nn.Linear(256, 256), nn.Tanh(),
+                            nn.Linear(256, 128))
+        ref = nn.Sequential(nn.Linear(128, 256), nn.BatchNorm1d(256, momentum=momentum), nn.Tanh(), nn.Linear(256, 256), nn.Tanh(),
+                            nn.Linear(256, 128)).double()
+        ref.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in ffn.state_dict().items()})
+        ffn = ffn.to(dev()).train(); ref.train()
+        for step in range(2):                                              # twice: running statistics accumulate
+            x = torch.randn(333, 128, generator=g, device=dev(), requires_grad=True)
+            up = torch.randn(333, 128, generator=g, device=dev())
+            out = dense.ffn_forward(ffn, x, True)
+            ffn.zero_grad(); (out * up).sum().backward()
+            x64 = x.detach().double().cpu().requires_grad_(True)
+            ref.zero_grad()
+            y64 = ref(x64)
+            (y64 * up.double().cpu()).sum().backward()
+            close(out, y64.detach().numpy(), what=f"ffn forward step {step}")
+            close(x.grad, x64.grad.numpy(), what=f"ffn dx step {step}")
+            for (k, v), (_, r) in zip(ffn.named_parameters(), ref.named_parameters()):
+                # 0.bias sits in front of BatchNorm: its gradient is mathematically zero, both sides hold rounding noise
+                close(v.grad, r.grad.numpy(), what=f"ffn grad {k} step {step}", atol=3e-6 if k == "0.bias" else 1e-9)
+        close(ffn[1].running_mean, ref[1].running_mean.numpy(), what=f"running_mean momentum={momentum}")
+        close(ffn[1].running_var, ref[1].running_var.numpy(), what=f"running_var momentum={momentum}")
+        assert int(ffn[1].num_batches_tracked) == int(ref[1].num_batches_tracked) == 2
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+        dense.ffn_forward(ffn, torch.randn(1, 128, device=dev()), True)
 
 
 def test_norm_kernels_match_float64():
