@@ -237,10 +237,12 @@ int pc_type_scores_topk(const float* a, int64_t m, int k, int64_t lda, const flo
 /* Two-layer MLP of type_transition.py:15-20 on gathered rows: x = table[idx[r]] (idx NULL: table[r]),
  * hidden = dropout(relu(W1 x + b1)), out = W2 hidden + b2.  W1 [hid, d_in], W2 [d_out, hid] row-major (nn.Linear
  * layout).  dropout_p in [0,1): counter-based mask from (seed, row, unit), survivors scaled by 1/(1-p) (torch's
- * Philox stream cannot be matched; pass 0 in eval mode).  `hidden` [rows, hid] is kept for the backward. */
+ * Philox stream cannot be matched; pass 0 in eval mode).  seed_dev (device uint64, may be NULL) is added to `seed` at
+ * run time: a step captured in a CUDA graph gets a fresh mask per replay by incrementing that counter inside the graph.
+ * `hidden` [rows, hid] is kept for the backward. */
 int pc_mlp2_fwd(const float* table, const int64_t* idx, int64_t rows, int d_in, int hid, int d_out, const float* w1,
-                const float* b1, const float* w2, const float* b2, float dropout_p, uint64_t seed, float* hidden,
-                float* out, pc_stream_t stream);
+                const float* b1, const float* w2, const float* b2, float dropout_p, uint64_t seed, const uint64_t* seed_dev,
+                float* hidden, float* out, pc_stream_t stream);
 /* Backward: d_x [rows, d_in] (may be NULL), d_w1, d_b1, d_w2, d_b2 (each may be NULL); the weight gradients are summed
  * per CTA in row order and then over the CTAs in CTA order (deterministic).  dropout_p as in the forward. */
 size_t pc_mlp2_bwd_workspace_bytes(int d_in, int hid, int d_out);

@@ -13,7 +13,8 @@ from .product2vec import Product2Vec
 from .retrieval import CatalogIndex, Metrics, ShardedCatalog
 from .data import ComplementaryDataset, GraphTripletSampler, SimilarityDataset, collate_fn
 from .inference import PCompanionInference
+from .graphs import GraphedTrainStep
 
 __all__ = ["ops", "BehaviorProductGraph", "Product2Vec", "ComplementaryTypeTransition",
            "ComplementaryItemPrediction", "PCompanion", "Metrics", "CatalogIndex", "ShardedCatalog",
-           "SimilarityDataset", "ComplementaryDataset", "collate_fn", "GraphTripletSampler", "PCompanionInference"]
+           "SimilarityDataset", "ComplementaryDataset", "collate_fn", "GraphTripletSampler", "PCompanionInference", "GraphedTrainStep"]

@@ -46,7 +46,7 @@ PROTOTYPES = {
     "pc_wgrad_tf32x3": (c_int, [P, c_int64, c_int, c_int64, P, c_int, c_int64, P, P, P, c_size_t, P]),
     "pc_type_scores_topk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "pc_type_scores_topk": (c_int, [P, c_int64, c_int, c_int64, P, c_int, P, c_int64, c_int, P, P, P, c_size_t, P]),
-    "pc_mlp2_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_uint64, P, P, P]),
+    "pc_mlp2_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_uint64, P, P, P, P]),
     "pc_mlp2_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pc_mlp2_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, P, P, c_float, P, P, P, P, P, P, c_size_t, P]),
     "pc_item_combine_fwd": (c_int, [P, P, c_int64, c_int, c_int, P, P]),

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(ML_WARPS * 32)
 mlp2_fwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, int64_t rows, int d_in, int hid, int d_out,
                 const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                 const float* __restrict__ b2, uint32_t drop_threshold, float inv_keep, uint64_t seed,
-                float* __restrict__ hidden, float* __restrict__ out) {
+                const uint64_t* __restrict__ seed_dev, float* __restrict__ hidden, float* __restrict__ out) {
+  if (seed_dev) seed += *seed_dev;      // per-replay seed of a CUDA-graph-captured step (the graph increments the counter)
   extern __shared__ float sm[];
   float* w1t = sm;                         // [d_in][hid]
   float* w2t = w1t + d_in * hid;           // [hid][d_out]
@@ -248,7 +249,7 @@ using namespace pc;
 
 extern "C" int pc_mlp2_fwd(const float* table, const int64_t* idx, int64_t rows, int d_in, int hid, int d_out,
                            const float* w1, const float* b1, const float* w2, const float* b2, float dropout_p,
-                           uint64_t seed, float* hidden, float* out, pc_stream_t stream) {
+                           uint64_t seed, const uint64_t* seed_dev, float* hidden, float* out, pc_stream_t stream) {
   if (int rc = mlp_check(rows, d_in, hid, d_out)) return rc;
   if (rows == 0) return PC_OK;
   PC_REQUIRE(table && w1 && w2 && hidden && out, PC_ERR_INVALID, "mlp2_fwd: null pointer");
@@ -259,7 +260,7 @@ extern "C" int pc_mlp2_fwd(const float* table, const int64_t* idx, int64_t rows,
   PC_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   PC_REQUIRE(smem <= 200 * 1024, PC_ERR_UNSUPPORTED, "mlp2_fwd: shared memory budget exceeded");
   mlp2_fwd_kernel<<<mlp_grid(rows), ML_WARPS * 32, smem, as_stream(stream)>>>(table, idx, rows, d_in, hid, d_out, w1, b1, w2, b2, thr,
-                                                                             1.f / (1.f - dropout_p), seed, hidden, out);
+                                                                             1.f / (1.f - dropout_p), seed, seed_dev, hidden, out);
   PC_LAUNCH_CHECK();
   return PC_OK;
 }

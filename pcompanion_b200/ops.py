@@ -520,7 +520,7 @@ class _MLP2(torch.autograd.Function):
     type_transition.py:15-20 (+ the nn.Embedding gather of p_companion.py:54) as one kernel each way."""
 
     @staticmethod
-    def forward(ctx, table, index, w1, b1, w2, b2, p_drop: float, seed: int):
+    def forward(ctx, table, index, w1, b1, w2, b2, p_drop: float, seed: int, seed_dev=None):
         table = table.contiguous()
         idx = None if index is None else index.reshape(-1).to(I64).contiguous()
         rows = table.shape[0] if idx is None else idx.numel()
@@ -530,8 +530,8 @@ class _MLP2(torch.autograd.Function):
         out = torch.empty(rows, d_out, dtype=F32, device=table.device)
         w1c, w2c = w1.contiguous(), w2.contiguous()
         call("pc_mlp2_fwd", dev(table, F32, "table"), dev(idx, I64, "index"), rows, d_in, hid, d_out, dev(w1c, F32, "w1"),
-             dev(b1, F32, "b1"), dev(w2c, F32, "w2"), dev(b2, F32, "b2"), float(p_drop), int(seed), dev(hidden, F32, "hidden"),
-             dev(out, F32, "out"), stream())
+             dev(b1, F32, "b1"), dev(w2c, F32, "w2"), dev(b2, F32, "b2"), float(p_drop), int(seed), dev(seed_dev, I64, "seed_dev"),
+             dev(hidden, F32, "hidden"), dev(out, F32, "out"), stream())
         ctx.save_for_backward(table, idx, hidden, w1c, w2c)
         ctx.p_drop = float(p_drop)
         ctx.has_bias = (b1 is not None, b2 is not None)
@@ -551,7 +551,7 @@ class _MLP2(torch.autograd.Function):
         d_b2 = torch.empty(n_out, dtype=F32, device=d_out.device) if ctx.has_bias[1] else None
         if rows == 0:
             return (torch.zeros_like(table) if need_x else None, None, torch.zeros_like(w1), None if d_b1 is None else d_b1.zero_(),
-                    torch.zeros_like(w2), None if d_b2 is None else d_b2.zero_(), None, None)
+                    torch.zeros_like(w2), None if d_b2 is None else d_b2.zero_(), None, None, None)
         ws = _lib.workspace(_lib.LIB.pc_mlp2_bwd_workspace_bytes(d_in, hid, n_out), d_out.device)
         call("pc_mlp2_bwd", dev(d_out, F32, "d_out"), dev(table, F32, "table"), dev(idx, I64, "index"), dev(hidden, F32, "hidden"),
              rows, d_in, hid, n_out, dev(w1, F32, "w1"), dev(w2, F32, "w2"), ctx.p_drop, dev(d_x, F32, "d_x"), dev(d_w1, F32, "d_w1"),
@@ -559,17 +559,19 @@ class _MLP2(torch.autograd.Function):
         d_table = None
         if need_x:
             d_table = d_x if idx is None else index_rows_grad(d_x, idx, table.shape[0])
-        return d_table, None, d_w1, d_b1, d_w2, d_b2, None, None
+        return d_table, None, d_w1, d_b1, d_w2, d_b2, None, None, None
 
 
 def mlp2_supported(d_in: int, hid: int, d_out: int) -> bool:
     return 4 <= d_in <= 256 and 1 <= hid <= 128 and 1 <= d_out <= 256
 
 
-def mlp2(table: torch.Tensor, index: Optional[torch.Tensor], w1, b1, w2, b2, p_drop: float = 0.0, seed: int = 0) -> torch.Tensor:
+def mlp2(table: torch.Tensor, index: Optional[torch.Tensor], w1, b1, w2, b2, p_drop: float = 0.0, seed: int = 0,
+         seed_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """seed_dev: optional int64 device scalar added to `seed` when the kernel runs (CUDA-graph replays, see graphs.py)."""
     if not table.is_cuda:
         raise RuntimeError(f"pcompanion_b200.ops.mlp2: input on {table.device}; CUDA only (no CPU fallback)")
-    return _MLP2.apply(table, index, w1, b1, w2, b2, float(p_drop), int(seed))
+    return _MLP2.apply(table, index, w1, b1, w2, b2, float(p_drop), int(seed), seed_dev)
 
 
 class _ItemCombine(torch.autograd.Function):

@@ -42,7 +42,12 @@ class ComplementaryTypeTransition(nn.Module):
 
     def _run(self, table, index):
         p, seed = _dropout_args(self, self.dropout.p)
-        return ops.mlp2(table, index, self.encoder.weight, self.encoder.bias, self.decoder.weight, self.decoder.bias, p, seed)
+        counter = getattr(self, "_replay_counter", None)       # set by graphs.GraphedTrainStep: fresh mask per graph replay
+        out = ops.mlp2(table, index, self.encoder.weight, self.encoder.bias, self.decoder.weight, self.decoder.bias, p, seed,
+                       counter if p > 0.0 else None)
+        if counter is not None and p > 0.0:
+            counter.add_(1)
+        return out
 
     def forward(self, query_type_embedding):
         if not query_type_embedding.is_cuda:

@@ -156,3 +156,51 @@ def test_pcompanion_forward_runs_no_library_gemm_at_reference_batch():
     assert not lib, f"library GEMM kernels on the P-Companion path: {lib}"
     assert any("linear_tf32x3_kernel" in n for n in names) and any("mlp2_fwd_kernel" in n for n in names)
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters() if p.requires_grad)
+
+
+def test_graphed_train_step_equals_eager_steps_and_redraws_dropout():
+    """GraphedTrainStep (whole P-Companion step in one CUDA graph): with dropout off, three replays leave exactly the
+    parameters of three eager steps (same kernels, same order); with dropout on, every replay draws a new mask."""
+    from pcompanion_b200 import GraphedTrainStep, PCompanion
+    g = torch.Generator().manual_seed(3)
+    table = torch.randn(5_000, 128, generator=g)
+    b, t = 256, 1_000
+
+    def make_batch(seed):
+        gg = torch.Generator().manual_seed(seed)
+        bt = {"query_ids": torch.randint(0, 5_000, (b,), generator=gg), "query_types": torch.randint(0, t, (b,), generator=gg),
+              "positive_types": torch.randint(0, t, (b, 1), generator=gg), "negative_types": torch.randint(0, t, (b, 1), generator=gg),
+              "positive_items": torch.randn(b, 128, generator=gg), "negative_items": torch.randn(b, 128, generator=gg)}
+        return {k: v.to(dev()) for k, v in bt.items()}
+
+    def fresh(dropout):
+        torch.manual_seed(5)
+        m = PCompanion(make_cfg(NUM_TYPES=t, DROPOUT=dropout), table).to(dev()).train()
+        return m, torch.optim.Adam([q for q in m.parameters() if q.requires_grad], lr=1e-3, capturable=True)
+
+    batches = [make_batch(s) for s in (1, 2, 3)]
+    eager, opt_e = fresh(0.0)
+    for bt in batches:
+        opt_e.zero_grad(set_to_none=True)
+        eager.compute_loss(bt, eager(bt)).backward()
+        opt_e.step()
+    graphed, opt_g = fresh(0.0)
+    state0 = {k: v.detach().clone() for k, v in graphed.state_dict().items()}
+    step = GraphedTrainStep(graphed, opt_g, batches[0])                # its warm-up steps move the weights and Adam state:
+    graphed.load_state_dict(state0)                                    # restore both before the comparison
+    for st in opt_g.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    losses = [float(step(bt)) for bt in batches]
+    assert all(np.isfinite(losses))
+    for (k, a), (_, r) in zip(graphed.named_parameters(), eager.named_parameters()):
+        if a.requires_grad:
+            assert torch.equal(a, r), f"graphed step differs from eager step in {k}"
+    step.release()
+    # dropout: same batch, learning rate 0 -> the loss only changes through the mask
+    m, _ = fresh(0.5)
+    opt0 = torch.optim.Adam([q for q in m.parameters() if q.requires_grad], lr=0.0, capturable=True)
+    step = GraphedTrainStep(m, opt0, batches[0])
+    seen = {float(step(batches[0])) for _ in range(4)}
+    assert len(seen) == 4, f"dropout mask was not redrawn between replays: {seen}"
