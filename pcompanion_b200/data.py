@@ -183,6 +183,10 @@ class GraphTripletSampler:
         self.anchor, self.positive = ops.unpack_keys(keys)          # int32, sorted by (anchor, positive)
         self.sim_rowptr, self.sim_col = ops.csr_from_sorted_keys(keys, self.num_nodes)
         self.device = keys.device
+        # pc_sample_negatives pads with -1 when an anchor has fewer than k_neg eligible products; sample() / epoch() hand
+        # their negatives to the indexed triplet loss, which would read table[-1]: refuse such graphs there (checked once)
+        max_similar = int((self.sim_rowptr[1:] - self.sim_rowptr[:-1]).max().item())
+        self.always_k = self.num_nodes - 1 - max_similar >= k_neg
 
     def __len__(self) -> int:
         return self.anchor.numel()
@@ -195,7 +199,13 @@ class GraphTripletSampler:
              dev(out, torch.int32, "out"), stream())
         return out
 
+    def _require_k(self) -> None:
+        if not self.always_k:
+            raise ValueError(f"GraphTripletSampler: some anchor has fewer than {self.k_neg} eligible negatives "
+                             f"({self.num_nodes} products); use negatives_for() and mask the -1 padding")
+
     def sample(self, batch_size: int, seed: int):
+        self._require_k()
         g = torch.Generator(device=self.device).manual_seed(int(seed))
         pick = torch.randint(0, len(self), (batch_size,), generator=g, device=self.device)
         a, p = self.anchor[pick], self.positive[pick]
@@ -204,6 +214,7 @@ class GraphTripletSampler:
 
     def epoch(self, batch_size: int, seed: int):
         """One pass over all similarity pairs in a seeded random order (the reference's shuffle=True loader)."""
+        self._require_k()
         g = torch.Generator(device=self.device).manual_seed(int(seed))
         perm = torch.randperm(len(self), generator=g, device=self.device)
         for i in range(0, len(self), batch_size):

@@ -79,16 +79,37 @@ class HaloPlan:
         be set up on this system; PC_HALO_TRANSPORT=nccl forces that."""
         if self.world == 1 or not self.send_idx.is_cuda or os.environ.get("PC_HALO_TRANSPORT", "") == "nccl":
             return False
-        ok = torch.ones(1, device=self.send_idx.device)
+        # Every collective below is reached by every rank: rank-local failures (import, capability, allocation) only
+        # set a flag, and the outcome is agreed on with an all-reduce(MIN) BEFORE the next collective is entered.
+        dev = self.send_idx.device
+
+        def agreed(ok: bool) -> bool:
+            flag = torch.full((1,), 1.0 if ok else 0.0, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            return bool(flag.item() > 0)
+
         try:
-            peer = PeerHalo(self, width)
-        except Exception as e:   # noqa: BLE001 - any failure (driver, container permissions) means: stay on NCCL
-            self.peer_error = f"{type(e).__name__}: {e}"
-            peer = None
-            ok.zero_()
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-        self.peer = peer if ok.item() > 0 else None
-        return self.peer is not None
+            import torch.distributed._symmetric_memory as symm
+            symm.empty(4, dtype=torch.float32, device=dev)             # rank-local probe: the allocator works here
+            err = None
+        except (ImportError, RuntimeError, AttributeError, NotImplementedError) as e:
+            err = f"{type(e).__name__}: {e}"
+        if not agreed(err is None):
+            self.peer_error = err or "symmetric memory unavailable on a peer rank"
+            return False
+        peer = PeerHalo.__new__(PeerHalo)
+        peer._gather_layout(self, width)                               # collective (all-gather of the halo counts)
+        try:
+            peer._allocate()                                           # rank-local
+            err = None
+        except (RuntimeError, MemoryError) as e:
+            err = f"{type(e).__name__}: {e}"
+        if not agreed(err is None):
+            self.peer_error = err or "symmetric allocation failed on a peer rank"
+            return False
+        peer._rendezvous()                                             # collective (exchange of the peer mappings)
+        self.peer = peer
+        return True
 
     @staticmethod
     def _unique_sorted(col: torch.Tensor) -> torch.Tensor:
@@ -155,20 +176,37 @@ class PeerHalo:
     contents) and after the last one (the stores have landed)."""
 
     def __init__(self, plan: "HaloPlan", width: int = 256):
-        import ctypes
-        import torch.distributed._symmetric_memory as symm
+        """All three phases in one go (every rank must call it; a rank-local failure raises).  HaloPlan.enable_peer_memory
+        runs the phases separately and agrees on the outcome between them."""
+        self._gather_layout(plan, width)
+        self._allocate()
+        self._rendezvous()
+
+    def _gather_layout(self, plan: "HaloPlan", width: int) -> None:
         self.plan, self.width = plan, width
-        world, rank, group = plan.world, plan.rank, plan.group if plan.group is not None else dist.group.WORLD
+        world, rank = plan.world, plan.rank
+        self._group = plan.group if plan.group is not None else dist.group.WORLD
         dev = plan.send_idx.device
         mine = torch.tensor(plan.recv_counts, dtype=torch.int64, device=dev)
         allc = torch.empty(world, world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allc, mine, group=group)
+        dist.all_gather_into_tensor(allc, mine, group=self._group)
         c = allc.tolist()                                             # c[q][p] = rows rank q receives from rank p
         n_loc = [plan.bounds[q + 1] - plan.bounds[q] for q in range(world)]
-        lay = peer_layout(c, n_loc, rank)
-        self.table_rows, self.return_rows = lay["table_rows"], lay["return_rows"]
-        self._kv = symm.empty(self.table_rows * width, dtype=torch.float32, device=dev)
-        self._ret = symm.empty(self.return_rows * width, dtype=torch.float32, device=dev)
+        self._lay = peer_layout(c, n_loc, rank)
+        self.table_rows, self.return_rows = self._lay["table_rows"], self._lay["return_rows"]
+
+    def _allocate(self) -> None:
+        import torch.distributed._symmetric_memory as symm
+        dev = self.plan.send_idx.device
+        self._kv = symm.empty(self.table_rows * self.width, dtype=torch.float32, device=dev)
+        self._ret = symm.empty(self.return_rows * self.width, dtype=torch.float32, device=dev)
+
+    def _rendezvous(self) -> None:
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        plan, width, lay, group = self.plan, self.width, self._lay, self._group
+        world, rank = plan.world, plan.rank
+        dev = plan.send_idx.device
         h_kv = symm.rendezvous(self._kv, group.group_name)
         h_ret = symm.rendezvous(self._ret, group.group_name)
         self._handles = (h_kv, h_ret)
@@ -184,7 +222,6 @@ class PeerHalo:
             view = h_ret.get_buffer(p, (self.return_rows, width), torch.float32)[dst0: dst0 + cnt] if cnt else None
             self._r_copy.append((lay["r_src"][p], cnt, view))
         self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._group = group
         self.version = 0
         self.side = torch.cuda.Stream(device=dev)
 

@@ -15,6 +15,11 @@ from conftest import load_golden, state_dict_from
 pytestmark = pytest.mark.gpu
 
 REL = 1e-5  # BASELINE.json north_star: "within 1e-5 relative in fp32"
+# Gradients compared with the reference's OWN float32 gradients (golden fixtures written by the real reference): two fp32
+# computations that are each within 1e-5 of the exact value can be 2e-5 apart.  profiles/r2_grad_error_probe.json
+# (profiles/grad_error_probe.py) measures both sides against float64 autograd: CUDA path <= 5.1e-6, the reference's own
+# float32 arithmetic <= 5.6e-6 on every tensor except the bias in front of BatchNorm (mathematically zero gradient).
+REL_VS_FP32 = 2e-5
 
 
 def dev():
@@ -350,7 +355,7 @@ def test_product2vec_train_step_matches_reference_golden():
     close(n, g["train_negative_emb"], what="negative")
     close(loss, g["train_loss"], what="loss")
     for k, v in m.named_parameters():
-        close(v.grad, g["grad/" + k], rel=5e-5, atol=1e-7, what="grad " + k)   # reference grads are themselves fp32
+        close(v.grad, g["grad/" + k], rel=REL_VS_FP32, atol=1e-7, what="grad " + k)   # reference grads are themselves fp32
     close(m.ffn[1].running_mean, g["train_running_mean"], what="running_mean")
     close(m.ffn[1].running_var, g["train_running_var"], what="running_var")
     assert int(m.ffn[1].num_batches_tracked) == int(g["train_num_batches_tracked"])
@@ -401,11 +406,11 @@ def test_forward_graph_train_matches_oracle_and_torch_port_grads():
         nb = col[rowptr[i]:rowptr[i + 1]]
         rows.append(pm.attend(h[i:i + 1], h[nb].unsqueeze(0))[0] if len(nb) else h[i])
     (torch.stack(rows) * torch.tensor(w, dtype=torch.float64)).sum().backward()
-    close(xt.grad, x64.grad.numpy(), rel=5e-5, what="dx")
+    close(xt.grad, x64.grad.numpy(), what="dx")
     for (k, v), (_, v64) in zip(m.named_parameters(), pm.named_parameters()):
         # ffn.0.bias sits in front of BatchNorm: its gradient is mathematically zero (sum of 150 terms that
         # cancel), both sides hold fp32 summation noise of ~1e-6 there
-        close(v.grad, v64.grad.numpy(), rel=5e-5, atol=3e-6 if k == "ffn.0.bias" else 1e-7, what="grad " + k)
+        close(v.grad, v64.grad.numpy(), atol=3e-6 if k == "ffn.0.bias" else 1e-7, what="grad " + k)
 
 
 # ----------------------------------------------------------------------------- (3) losses / PCompanion
@@ -455,7 +460,7 @@ def test_pcompanion_matches_reference_golden():
     close(loss, g["loss"], what="loss")
     for k, v in m.named_parameters():
         if v.grad is not None:
-            close(v.grad, g["grad/" + k], rel=5e-5, atol=1e-7, what="grad " + k)
+            close(v.grad, g["grad/" + k], rel=REL_VS_FP32, atol=1e-7, what="grad " + k)
     with pytest.raises(KeyError):
         m({**batch, "query_ids": ["nope"] * len(batch["query_ids"])})
     # dense-table constructor + index tensor ids give the same numbers
@@ -627,9 +632,9 @@ def test_fused_graph_layer_equals_unfused_path_and_single_rank_partition():
                          ("partitioned", lambda xt: forward_graph_partitioned(m, xt, plan))):
             got = run(fn, train)
             close(got[0], ref[0].double().cpu().numpy(), what=f"{name} out train={train}")
-            close(got[1], ref[1].double().cpu().numpy(), rel=5e-5, what=f"{name} dx train={train}")
+            close(got[1], ref[1].double().cpu().numpy(), rel=REL_VS_FP32, what=f"{name} dx train={train}")   # two fp32 paths
             for (k, _), a, r in zip(m.named_parameters(), got[2], ref[2]):
-                close(a, r.double().cpu().numpy(), rel=5e-5, atol=3e-6 if k == "ffn.0.bias" else 1e-7, what=f"{name} grad {k} train={train}")
+                close(a, r.double().cpu().numpy(), rel=REL_VS_FP32, atol=3e-6 if k == "ffn.0.bias" else 1e-7, what=f"{name} grad {k} train={train}")
             close(got[3], ref[3].double().cpu().numpy(), what="running_mean")
             close(got[4], ref[4].double().cpu().numpy(), what="running_var")
 
