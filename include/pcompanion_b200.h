@@ -106,10 +106,13 @@ int pc_gat_bwd_dst(const float* q, int64_t ld_q, const float* kv, const int64_t*
  * first so the multi-GPU path can start returning halo gradients while the dst-major pass computes. */
 int pc_gat_delta(const float* o, const float* d_o, int64_t ld_do, int64_t n, int heads, float* stats, pc_stream_t stream);
 /* src-major backward over the CSC (colptr [n_src+1], row [E] = dst ids per src, ascending):
- * dkv [n_src, 256]. */
+ * dkv [n_src, 256].  A RANGE of source columns [c0, c0 + n) is processed by passing colptr + c0, kv + c0 * 256,
+ * dkv + c0 * ld_dkv, n and src_base = c0 (colptr holds absolute offsets into `row`; src_base keeps the dropout
+ * mask keyed on the true column id): the multi-GPU backward runs one range per halo owner so that each owner's
+ * partials start travelling while the next range is computed. */
 int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, const int64_t* colptr, const int32_t* row,
                    int64_t n_src, int heads, float dropout_p, uint64_t seed, const float* d_o, int64_t ld_do,
-                   const float* stats, float* dkv, int64_t ld_dkv, pc_stream_t stream);
+                   const float* stats, float* dkv, int64_t ld_dkv, int64_t src_base, pc_stream_t stream);
 
 /* Dense row projection on the tensor cores (tcgen05, 3xTF32 split => fp32-faithful, see gemm.cu):
  *   Y[m, n] = epilogue( A[m, k] . W[n, k]^T + bias[n] )

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3)
 gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, const int64_t* __restrict__ colptr,
                         const int32_t* __restrict__ row, int64_t n_src, int64_t ldq4, int64_t lddo4, int64_t lddkv4, float scale,
                         DropArgs drop, const float4* __restrict__ dO, const float* __restrict__ stats, float4* __restrict__ dKV,
-                        int packed) {
+                        int packed, int64_t src_base) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   constexpr int G = 32 / H;
   // the 2H floats of stats ride along as 16-byte (8 for H = 1) cp.async copies issued by the requesting lane and
@@ -334,7 +334,7 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
               float pk = p;
               if (DROP) {
                 const int dst = __shfl_sync(FULL, my_row, (t + u) & 31);
-                const float ks = keep_scale(drop.seed, uint32_t(dst), uint32_t(j), head, drop.threshold, drop.inv_keep);
+                const float ks = keep_scale(drop.seed, uint32_t(dst), uint32_t(j + src_base), head, drop.threshold, drop.inv_keep);
                 da *= ks;
                 pk *= ks;
               }
@@ -467,7 +467,7 @@ extern "C" int pc_gat_bwd_dst(const float* q, int64_t ld_q, const float* kv, con
 
 extern "C" int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, const int64_t* colptr, const int32_t* row,
                               int64_t n_src, int heads, float dropout_p, uint64_t seed, const float* d_o, int64_t ld_do,
-                              const float* stats, float* dkv, int64_t ld_dkv, pc_stream_t stream) {
+                              const float* stats, float* dkv, int64_t ld_dkv, int64_t src_base, pc_stream_t stream) {
   if (int rc = check_common(kv, colptr, dkv, stats, n_src, heads, dropout_p)) return rc;
   PC_REQUIRE(ld_q >= 128 && ld_q % 4 == 0 && ld_do >= 128 && ld_do % 4 == 0 && ld_dkv >= 256 && ld_dkv % 4 == 0, PC_ERR_INVALID,
              "gat_bwd_src: leading dimensions must be multiples of 4 (q, d_o >= 128, dkv >= 256)");
@@ -484,7 +484,7 @@ extern "C" int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, con
   gat_bwd_src_kernel<H, RU_SRC, DROP><<<grid, WARPS * 32, RING_SMEM_QG, st>>>(                      \
       reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(kv), colptr, row, n_src,       \
       ld_q / 4, ld_do / 4, ld_dkv / 4, scale,                                                            \
-      drop, reinterpret_cast<const float4*>(d_o), stats, reinterpret_cast<float4*>(dkv), packed)
+      drop, reinterpret_cast<const float4*>(d_o), stats, reinterpret_cast<float4*>(dkv), packed, src_base)
   if (dropout_p > 0.f) {
     PC_DISPATCH_HEADS(heads, true, CALL_BS)
   } else {

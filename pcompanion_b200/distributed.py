@@ -243,15 +243,30 @@ class PeerHalo:
              dev(self.plan.send_idx, torch.int64, "send_idx"), self.plan.world, self._f_off, self._f_base, None, self._f_dst,
              self._f_first, self.width, stream())
 
+    def reverse_runs(self):
+        """(owner, first column, count) of every non-empty run of halo columns in the [local | halo] table, in the staggered
+        order the copies are issued (rank r starts with owner r + 1)."""
+        world, rank = self.plan.world, self.plan.rank
+        out = []
+        for k in range(1, world + 1):
+            p = (rank + k) % world
+            src0, cnt, _ = self._r_copy[p]
+            if cnt:
+                out.append((p, src0, cnt))
+        return out
+
+    def push_reverse_run(self, dkv_ext: torch.Tensor, owner: int) -> None:
+        """One owner's run of halo partials -> its return buffer, as a plain peer copy on the copy engines (current stream)."""
+        src0, cnt, view = self._r_copy[owner]
+        if cnt:
+            view.copy_(dkv_ext[src0: src0 + cnt])
+
     def push_reverse(self, dkv_ext: torch.Tensor) -> None:
         """Every owner's run of halo partials is contiguous on both sides, so it travels as a plain peer copy on the
         copy engines: the SMs stay with the dst-major pass and the GEMMs this overlaps with.  (pc_halo_push with
         index = NULL does the same from the SMs: measured 9 -> 4.6 ms of wgrad slowdown at 4 GPUs, so not used here.)"""
-        world, rank = self.plan.world, self.plan.rank
-        for k in range(1, world + 1):                                 # staggered: rank r starts with owner r+1
-            src0, cnt, view = self._r_copy[(rank + k) % world]
-            if cnt:
-                view.copy_(dkv_ext[src0: src0 + cnt])
+        for owner, _, _ in self.reverse_runs():
+            self.push_reverse_run(dkv_ext, owner)
 
 
 class _HaloGather(torch.autograd.Function):

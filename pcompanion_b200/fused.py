@@ -202,21 +202,30 @@ class _P2VGraphLayer(torch.autograd.Function):
             dq = torch.empty(n, 128, dtype=F32, device=x.device)
             dkv = torch.empty(graph.n_cols, 256, dtype=F32, device=x.device)
             ops.gat_delta_raw(o, qg[:, 128:], heads, stats)
-            ops.gat_bwd_src_raw(qg[:, :128], kv, graph, heads, p_drop, seed, qg[:, 128:], stats, dkv)
             peer = plan.peer
+            src_args = (qg[:, :128], kv, graph, heads, p_drop, seed, qg[:, 128:], stats, dkv)
             if peer is not None:
                 if peer.version != cfg["kv_version"]:
                     raise RuntimeError("p2v_graph_layer.backward: the symmetric K|V table was overwritten by a later forward "
                                        "on the same HaloPlan; run backward before the next forward")
+                # halo columns first, ONE RANGE PER OWNER (each owner's columns are contiguous): a range's partials start
+                # travelling to their owner on the copy engines (side stream) while the next range is computed; the
+                # local columns and the dst-major pass follow, so the whole return path hides behind ~10 ms of compute
                 main = torch.cuda.current_stream()
-                peer.side.wait_stream(main)
-                with torch.cuda.stream(peer.side):           # partials travel while the dst-major pass runs
-                    peer.push_reverse(dkv)
+                for owner, c0, cnt in peer.reverse_runs():
+                    ops.gat_bwd_src_raw(*src_args, col_begin=c0, col_count=cnt)
+                    peer.side.wait_stream(main)
+                    with torch.cuda.stream(peer.side):
+                        peer.push_reverse_run(dkv, owner)
+                with torch.cuda.stream(peer.side):
                     peer.barrier()
+                ops.gat_bwd_src_raw(*src_args, col_begin=0, col_count=n)
                 returned, work = peer.returned(), None
             else:
+                ops.gat_bwd_src_raw(*src_args, col_begin=n)               # halo columns, then their all-to-all ...
                 returned = torch.empty(plan.send_idx.numel(), 256, dtype=F32, device=x.device)
                 work = plan.reverse_exchange(dkv[n:], returned, async_op=True)
+                ops.gat_bwd_src_raw(*src_args, col_begin=0, col_count=n)  # ... travels while the local columns are computed
             ops.gat_bwd_dst_raw(qg[:, :128], kv, graph, heads, p_drop, seed, o, qg[:, 128:], stats, dq)
             dw_q, db_q = ops.wgrad_tc(dq, h)
             w_in_t = w_in.t().contiguous()                                            # [128, 384]

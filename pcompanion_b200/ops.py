@@ -185,12 +185,19 @@ def gat_bwd_dst_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, o, d_o, st
          _f32_cuda(d_o, "d_o"), d_o.stride(0), dev(stats, F32, "stats"), _f32_cuda(dq, "dq"), dq.stride(0), stream())
 
 
-def gat_bwd_src_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, d_o, stats, dkv) -> None:
-    """needs stats[:,1,:] (delta) from pc_gat_bwd_dst or pc_gat_delta"""
+def gat_bwd_src_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, d_o, stats, dkv, col_begin: int = 0,
+                    col_count: Optional[int] = None) -> None:
+    """needs stats[:,1,:] (delta) from pc_gat_bwd_dst or pc_gat_delta.  (col_begin, col_count) restricts the pass to a
+    range of source columns (rows col_begin.. of kv / dkv)."""
     colptr, row = graph.transposed()
-    call("pc_gat_bwd_src", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(colptr, I64, "colptr"),
-         dev(row, I32, "row"), graph.n_cols, heads, float(dropout_p), int(seed), _f32_cuda(d_o, "d_o"), d_o.stride(0),
-         dev(stats, F32, "stats"), _f32_cuda(dkv, "dkv"), dkv.stride(0), stream())
+    if col_count is None:
+        col_count = graph.n_cols - col_begin
+    if col_count <= 0:
+        return
+    kv_r, dkv_r = kv[col_begin: col_begin + col_count], dkv[col_begin: col_begin + col_count]
+    call("pc_gat_bwd_src", _f32_cuda(q, "q"), q.stride(0), dev(kv_r, F32, "kv"), dev(colptr[col_begin: col_begin + col_count + 1], I64, "colptr"),
+         dev(row, I32, "row"), col_count, heads, float(dropout_p), int(seed), _f32_cuda(d_o, "d_o"), d_o.stride(0),
+         dev(stats, F32, "stats"), _f32_cuda(dkv_r, "dkv"), dkv_r.stride(0), int(col_begin), stream())
 
 
 def gat_bwd_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, o, d_o, stats, dq, dkv) -> None:
