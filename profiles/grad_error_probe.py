@@ -67,7 +67,7 @@ def main():
             runs[name] = port_run(pm, x, w, rowptr, col, dtype)
         o64, dx64, g64 = runs["f64"]
         o32, dx32, g32 = runs["f32"]
-        floor = float(np.abs(g64["ffn.0.weight"]).max()) * 1e-2
+        floor = float(np.abs(g64["ffn.0.weight"]).max())
         rec = {"forward": {"cuda": rel_err(out.detach().cpu().numpy(), o64), "reference_fp32": rel_err(o32, o64)},
                "dx": {"cuda": rel_err(xt.grad.cpu().numpy(), dx64), "reference_fp32": rel_err(dx32, dx64)}}
         for k, v in m.named_parameters():
@@ -78,7 +78,7 @@ def main():
     worst_ref = max(v["reference_fp32"] for r in report.values() for v in r.values())
     report["worst"] = {"cuda": worst_cuda, "reference_fp32": worst_ref,
                        "metric": "max |a - r| / (|r| + rms(r)) against float64 autograd; ffn.0.bias (mathematically zero gradient in "
-                                 "front of BatchNorm) with a floor of 1 % of max |grad ffn.0.weight|"}
+                                 "front of BatchNorm) measured against the scale of the neighbouring weight gradient: floor = max |grad ffn.0.weight|"}
     print(json.dumps(report, indent=1))
 
 

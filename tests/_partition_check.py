@@ -19,7 +19,7 @@ REL = 1e-5
 
 def rel_err(a: torch.Tensor, r: torch.Tensor, floor: float = 0.0) -> float:
     """max |a - r| / (|r| + rms(r) + floor): the 1e-5 gate of tests/test_gpu_parity.close as one number."""
-    a, r = a.double(), r.double()
+    a, r = a.detach().double(), r.detach().double()
     scale = float(torch.sqrt(torch.mean(r * r))) if r.numel() else 0.0
     return float(((a - r).abs() / (r.abs() + scale + floor + 1e-30)).max()) if r.numel() else 0.0
 
@@ -74,10 +74,11 @@ def check_partitioned(rank: int, world: int, dev: torch.device, n: int = 3000, r
         return o
 
     def grad_errs(m, ref):
-        floor = float(ref["ffn.0.weight"].abs().max()) * 1e-2
+        floor = float(ref["ffn.0.weight"].abs().max())
         errs = {}
         for k, p in m.named_parameters():
-            # ffn.0.bias sits in front of BatchNorm: its gradient is mathematically zero, only summation noise
+            # ffn.0.bias sits in front of BatchNorm: its gradient is mathematically zero, both sides hold only the fp32
+            # summation noise of terms that cancel - measured against the scale of the neighbouring weight gradient
             errs[k] = rel_err(p.grad, ref[k], floor if k == "ffn.0.bias" else 0.0)
         return errs
 
