@@ -141,6 +141,22 @@ class L2Flush:
         self.buf.zero_()
 
 
+def warm_up(fn, min_steps, min_seconds, dev, world):
+    """At least `min_steps` untimed calls AND about `min_seconds` of them (short steps must not be timed on a GPU that is
+    still ramping its clocks).  The number of extra calls is derived from the max-over-ranks elapsed time, so every rank
+    runs the SAME count - fn may contain collectives."""
+    t0 = time.perf_counter()
+    for _ in range(min_steps):
+        fn()
+    torch.cuda.synchronize()
+    elapsed = max_over_ranks([time.perf_counter() - t0], dev, world)[0]
+    if elapsed < min_seconds:
+        extra = min(int(math.ceil((min_seconds - elapsed) / max(elapsed / max(min_steps, 1), 1e-5))), 2000)
+        for _ in range(extra):
+            fn()
+        torch.cuda.synchronize()
+
+
 def timed_steps(fn, steps, dev, world, flush=None):
     """Average device time of `steps` calls of fn (CUDA events on the current stream, barrier + synchronize on both sides,
     max over ranks).  With `flush` every step is timed on its own and the L2 flush between the steps is not."""
@@ -504,11 +520,7 @@ def pcompanion_leg(args, rank, world, dev, batch, cpu=False):
     small = b * t * 4 < (512 << 20)
     flush = L2Flush(dev) if small else None
     sampler = ClockSampler(dev.index)
-    t_warm, n_warm = time.perf_counter(), 0
-    while n_warm < args.warmup or time.perf_counter() - t_warm < 1.0:
-        step(bt_dev)
-        torch.cuda.synchronize()
-        n_warm += 1
+    warm_up(lambda: step(bt_dev), args.warmup, 1.0, dev, world)
     sampler.mark()
     l0 = _lib.LAUNCHES
     ms, _ = timed_steps(lambda: step(bt_dev), args.steps, dev, world, flush)
@@ -626,11 +638,7 @@ def retrieval_leg(args, rank, world, dev, dense=False, cpu=False):
     # a step is only a few ms: warm up for at least W steps AND ~0.5 s, so that the timed region does not start on a GPU
     # that is still ramping its clocks after the host-side setup
     sampler = ClockSampler(dev.index)
-    t_warm, n_warm = time.perf_counter(), 0
-    while n_warm < args.warmup or time.perf_counter() - t_warm < 0.5:
-        step()
-        torch.cuda.synchronize()
-        n_warm += 1
+    warm_up(step, args.warmup, 1.5, dev, world)
     sampler.mark()
     launches0 = _lib.LAUNCHES
     _lib.PROFILE = []
