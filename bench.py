@@ -2,7 +2,7 @@
 """Benchmark of the P-Companion hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload all|gat|retrieval|retrieval_dense|pcompanion|c1|c5]
+                    [--workload all|gat|gat_skewed|retrieval|retrieval_dense|pcompanion|c1|c5]
 
 BASELINE.json's metric has two halves - "GAT edges/sec fwd+bwd (Product2Vec) & top-K queries/sec at 1/2/4/8 B200" -
 so the default run (`--workload all`) measures both and prints ONE JSON line on rank 0:
@@ -13,7 +13,8 @@ so the default run (`--workload all`) measures both and prints ONE JSON line on 
   exchange and the line carries the multi-GPU parity check that ran before the timing;
 * `retrieval` (C4: masked top-10 over a 10 M-product catalog, 1 K types, sharded over the ranks) and, at N = 1,
   `retrieval_dense` (the north-star's tensor-core wording of the same query) - `topk_queries_per_sec` repeats the value;
-* `pcompanion` (C3: joint P-Companion step on a 1 M-product table, 34,800 types, batch 256 and 65,536).
+* `pcompanion` (C3: joint P-Companion step on a 1 M-product table, 34,800 types, batch 256 and 65,536);
+* at N = 1 also `gat_skewed` (the same step on a power-law graph, hub splitting on / off) and `c1` (configs[0]).
 
 Every sub-record has its own value / ms_per_step / roofline / e2e (/ cpu_baseline at N = 1).
 """
@@ -326,6 +327,66 @@ def gat_single(args, dev):
                 "h2d_bytes_per_step": x_host.numel() * 4 + trip_host.numel() * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "loss": float(loss.item()),
     }
+
+
+# ============================================================================= GAT leg on a skewed-degree graph
+def gat_skewed_leg(args, dev):
+    """Same Product2Vec step on a power-law graph: 1 M products, ~20 M co-view edges, out-degrees and in-degrees Pareto
+    (alpha 1.5) - a handful of products with 10^4..10^5 neighbours.  Timed with hub splitting (ops.HUB_THRESHOLD) and with
+    one warp per row regardless of its degree."""
+    import pcompanion_b200 as pc
+    from pcompanion_b200 import _lib, ops
+    n = NODES_PER_GPU
+    g = torch.Generator(device=dev).manual_seed(SEED + 11)
+    alpha, xm = 1.5, EDGES_PER_GPU / NODES_PER_GPU / 3.0
+    deg = (xm * torch.rand(n, generator=g, device=dev).clamp_(min=1e-7).pow(-1.0 / alpha)).long().clamp_(max=n // 8)
+    src = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int32), deg)
+    wcol = torch.rand(n, generator=g, device=dev).clamp_(min=1e-7).pow(-1.0 / alpha)
+    cdf = torch.cumsum(wcol.double(), 0)
+    dst = torch.searchsorted(cdf, torch.rand(src.numel(), generator=g, device=dev, dtype=torch.float64) * cdf[-1]).clamp_(max=n - 1).to(torch.int32)
+    base, _ = ops.build_csr(src, dst, n)
+    del src, dst, cdf
+    base.transposed()
+    e = base.num_edges
+    out_deg = base.rowptr[1:] - base.rowptr[:-1]
+    colptr, _ = base.transposed()
+    in_deg = colptr[1:] - colptr[:-1]
+    cfg = make_cfg(dev)
+    x = torch.randn(n, 128, generator=g, device=dev)
+    trip = torch.randint(0, n, (TRIPLETS, 2 + KNEG), generator=g, device=dev)
+    res = {}
+    for name, split in (("hub_split", True), ("one_warp_per_row", False)):
+        graph = ops.CSRGraph(base.rowptr, base.col, n, n, base._t, split_hubs=split)
+        torch.manual_seed(SEED)
+        model = pc.Product2Vec(cfg).to(dev).train()
+        opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+
+        def step():
+            emb = model.forward_graph(x, graph)
+            loss = model.triplet_loss_indexed(emb, trip[:, 0], trip[:, 1], trip[:, 2:])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(args.warmup):
+            step()
+        _lib.PROFILE = []
+        ms, loss = timed_steps(step, args.steps, dev, 1)
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        per = {}
+        for nm, s0, s1 in prof:
+            per[nm] = per.get(nm, 0.0) + s0.elapsed_time(s1) / args.steps
+        res[name] = {"ms_per_step": ms, "edges_per_s": e / (ms * 1e-3), "loss": float(loss.item()),
+                     "gat_ms": {k: round(v, 3) for k, v in per.items() if k.startswith("pc_gat") or k == "pc_rows_segment_sum"}}
+    hs, hst = ops.CSRGraph(base.rowptr, base.col, n, n, base._t).hub_split(), ops.CSRGraph(base.rowptr, base.col, n, n, base._t).hub_split_t()
+    return {"metric": "gat_edges_per_sec_fwd_bwd_skewed", "value": res["hub_split"]["edges_per_s"], "unit": "edges/s", "n_gpus": 1,
+            "ms_per_step": res["hub_split"]["ms_per_step"],
+            "config": {"workload": "power-law BPG: 1M products, Pareto(1.5) out- and in-degrees, Product2Vec full-graph GAT fwd+bwd + "
+                                   "triplet hinge + Adam", "nodes": n, "edges": e, "max_out_degree": int(out_deg.max().item()),
+                       "max_in_degree": int(in_deg.max().item()), "hub_threshold": ops.HUB_THRESHOLD, "hub_segment": ops.HUB_SEGMENT,
+                       "hub_rows": 0 if hs is None else int(hs.hub_rows.numel()), "hub_columns": 0 if hst is None else int(hst.hub_rows.numel()),
+                       "virtual_rows": 0 if hs is None else hs.n_virtual, "virtual_columns": 0 if hst is None else hst.n_virtual},
+            "variants": res, "speedup_from_hub_split": res["one_warp_per_row"]["ms_per_step"] / res["hub_split"]["ms_per_step"]}
 
 
 # ============================================================================= GAT leg, node-partitioned (N > 1)
@@ -960,6 +1021,13 @@ def run_ours(args):
             line = recs[f"b{args.batch}"]
         elif line is not None:
             line["pcompanion"] = recs
+    if wl in ("all", "gat_skewed") and world == 1:
+        r = gat_skewed_leg(args, dev)
+        free()
+        if wl == "gat_skewed":
+            line = r
+        elif line is not None:
+            line["gat_skewed"] = r
     if wl in ("all", "c1") and world == 1:
         r = c1_leg(args, dev, cpu=cpu)
         free()
@@ -1053,7 +1121,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "gat", "retrieval", "retrieval_dense", "pcompanion", "c1", "c5"])
+    ap.add_argument("--workload", default="all", choices=["all", "gat", "gat_skewed", "retrieval", "retrieval_dense", "pcompanion", "c1", "c5"])
     ap.add_argument("--batch", type=int, default=4096, help="pcompanion: samples per GPU per step")
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--skip-cpu", action="store_true", help="skip the CPU-baseline legs (profiling runs)")

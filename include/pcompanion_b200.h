@@ -95,13 +95,14 @@ int pc_csr_transpose_keys(const int64_t* rowptr, const int32_t* col, int64_t n_r
  * (fixed summation order per row, no float atomics). */
 /* q, d_o, dq and dkv carry a row stride in floats (ld_*), so Q and dO can be the two halves of one
  * [n, 256] buffer (one 1 KiB gather per edge in the src-major backward) and dQ | dK|dV the
- * column blocks of one [n, 384] buffer (a single K=384 dgrad GEMM for the packed in-projection). */
+ * column blocks of one [n, 384] buffer (a single K=384 dgrad GEMM for the packed in-projection).
+ * dst_ids (int32 [n_dst], may be NULL): node id of row r for the dropout mask when the rows are virtual (see hub nodes). */
 int pc_gat_fwd(const float* q, int64_t ld_q, const float* kv, const int64_t* rowptr, const int32_t* col, int64_t n_dst,
-               int heads, float dropout_p, uint64_t seed, float* o, float* stats, pc_stream_t stream);
+               int heads, float dropout_p, uint64_t seed, const int32_t* dst_ids, float* o, float* stats, pc_stream_t stream);
 /* dst-major backward: dq [n_dst,128]; fills stats[:,1,:]. */
 int pc_gat_bwd_dst(const float* q, int64_t ld_q, const float* kv, const int64_t* rowptr, const int32_t* col,
-                   int64_t n_dst, int heads, float dropout_p, uint64_t seed, const float* o, const float* d_o,
-                   int64_t ld_do, float* stats, float* dq, int64_t ld_dq, pc_stream_t stream);
+                   int64_t n_dst, int heads, float dropout_p, uint64_t seed, const int32_t* dst_ids, const float* o,
+                   const float* d_o, int64_t ld_do, float* stats, float* dq, int64_t ld_dq, pc_stream_t stream);
 /* stats[:,1,:] = dO . O per head on its own (pc_gat_bwd_dst also writes it); lets the src-major pass run
  * first so the multi-GPU path can start returning halo gradients while the dst-major pass computes. */
 int pc_gat_delta(const float* o, const float* d_o, int64_t ld_do, int64_t n, int heads, float* stats, pc_stream_t stream);
@@ -112,7 +113,17 @@ int pc_gat_delta(const float* o, const float* d_o, int64_t ld_do, int64_t n, int
  * partials start travelling while the next range is computed. */
 int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, const int64_t* colptr, const int32_t* row,
                    int64_t n_src, int heads, float dropout_p, uint64_t seed, const float* d_o, int64_t ld_do,
-                   const float* stats, float* dkv, int64_t ld_dkv, int64_t src_base, pc_stream_t stream);
+                   const float* stats, float* dkv, int64_t ld_dkv, int64_t src_base, const int32_t* src_ids,
+                   pc_stream_t stream);
+/* Hub nodes.  One warp walks one CSR row, so a row with 10^5 neighbours would take tens of milliseconds on
+ * its own.  The host splits such rows into "virtual rows" - consecutive slices of the row's neighbour list, listed in
+ * a small second CSR - and runs the same kernels on them (dst_ids / src_ids give the real node id of a virtual row
+ * for the dropout mask; NULL = the row index itself).  pc_gat_merge_segments folds the per-slice softmax states back
+ * into the row: O = sum_v O_v 2^(lse_v - lse), lse = log2 sum_v 2^(lse_v), slices in ascending order (deterministic);
+ * virtual rows [seg_ptr[h], seg_ptr[h+1]) belong to row hub_rows[h].  The backward partial gradients of the slices
+ * are summed with pc_rows_segment_sum. */
+int pc_gat_merge_segments(const float* o_seg, const float* stats_seg, const int64_t* seg_ptr, const int64_t* hub_rows,
+                          int64_t n_hubs, int heads, float* o, float* stats, pc_stream_t stream);
 
 /* Dense row projection on the tensor cores (tcgen05, 3xTF32 split => fp32-faithful, see gemm.cu):
  *   Y[m, n] = epilogue( A[m, k] . W[n, k]^T + bias[n] )

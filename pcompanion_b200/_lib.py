@@ -30,9 +30,10 @@ PROTOTYPES = {
     "pc_set_filter_sorted": (c_int, [P, c_int64, P, c_int64, c_int, P, P, P, c_size_t, P]),
     "pc_csr_from_sorted_keys": (c_int, [P, c_int64, c_int64, P, P, P]),
     "pc_csr_transpose_keys": (c_int, [P, P, c_int64, c_int64, P, P]),
-    "pc_gat_fwd": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_float, c_uint64, P, P, P]),
-    "pc_gat_bwd_dst": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_float, c_uint64, P, P, c_int64, P, P, c_int64, P]),
-    "pc_gat_bwd_src": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_float, c_uint64, P, c_int64, P, P, c_int64, c_int64, P]),
+    "pc_gat_fwd": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_float, c_uint64, P, P, P, P]),
+    "pc_gat_bwd_dst": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_float, c_uint64, P, P, P, c_int64, P, P, c_int64, P]),
+    "pc_gat_bwd_src": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_float, c_uint64, P, c_int64, P, P, c_int64, c_int64, P, P]),
+    "pc_gat_merge_segments": (c_int, [P, P, P, P, c_int64, c_int, P, P, P]),
     "pc_gat_delta": (c_int, [P, P, c_int64, c_int64, c_int, P, P]),
     "pc_col_reduce_workspace_bytes": (c_size_t, [c_int]),
     "pc_col_stats": (c_int, [P, c_int64, c_int, c_int64, P, P, c_size_t, P]),

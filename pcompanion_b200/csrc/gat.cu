@@ -101,7 +101,7 @@ template <int H, int U, bool DROP>
 __global__ void __launch_bounds__(WARPS * 32, 3)
 gat_fwd_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, const int64_t* __restrict__ rowptr,
                     const int32_t* __restrict__ col, int64_t n_dst, int64_t ldq4, float scale_log2e, DropArgs drop,
-                    float4* __restrict__ O, float* __restrict__ stats) {
+                    const int32_t* __restrict__ dst_ids, float4* __restrict__ O, float* __restrict__ stats) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   constexpr int G = 32 / H;
   const int lane = lane_id(), warp = warp_id();
@@ -119,6 +119,7 @@ gat_fwd_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, cons
   float4 q_next = ldg4(Q + r0 * ldq4 + lane);
   for (int r = 0; r < rows; ++r) {
     const int64_t i = r0 + r;
+    const uint32_t i_id = DROP ? uint32_t(dst_ids ? dst_ids[i] : i) : 0u;   // virtual rows of a split hub keep the hub's id
     const float4 q = scale4(q_next, scale_log2e);
     if (r + 1 < rows) q_next = ldg4(Q + (i + 1) * ldq4 + lane);
     const int beg = __shfl_sync(FULL, my_rel, r), end = __shfl_sync(FULL, my_rel, r + 1);
@@ -160,7 +161,7 @@ gat_fwd_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, cons
             float pv = p;
             if (DROP) {
               const int src = __shfl_sync(FULL, my_col, (t + u) & 31);
-              pv *= keep_scale(drop.seed, uint32_t(i), uint32_t(src), head, drop.threshold, drop.inv_keep);
+              pv *= keep_scale(drop.seed, i_id, uint32_t(src), head, drop.threshold, drop.inv_keep);
             }
             fma4(acc, pv, v[u]);
           }
@@ -186,8 +187,8 @@ template <int H, int U, bool DROP>
 __global__ void __launch_bounds__(WARPS * 32, 3)
 gat_bwd_dst_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, const int64_t* __restrict__ rowptr,
                         const int32_t* __restrict__ col, int64_t n_dst, int64_t ldq4, int64_t lddo4, int64_t lddq4, float scale,
-                        DropArgs drop, const float4* __restrict__ O, const float4* __restrict__ dO, float* __restrict__ stats,
-                        float4* __restrict__ dQ) {
+                        DropArgs drop, const int32_t* __restrict__ dst_ids, const float4* __restrict__ O,
+                        const float4* __restrict__ dO, float* __restrict__ stats, float4* __restrict__ dQ) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   constexpr int G = 32 / H;
   const int lane = lane_id(), warp = warp_id();
@@ -204,6 +205,7 @@ gat_bwd_dst_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
   PC_RING_ISSUE_KV(RING)
   for (int r = 0; r < rows; ++r) {
     const int64_t i = r0 + r;
+    const uint32_t i_id = DROP ? uint32_t(dst_ids ? dst_ids[i] : i) : 0u;
     const float4 q = scale4(ldg4(Q + i * ldq4 + lane), scale * LOG2E);
     const float4 go = ldg4(dO + i * lddo4 + lane);
     const float4 o = ldg4(O + i * ROW4 + lane);
@@ -236,7 +238,7 @@ gat_bwd_dst_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
             float da = group_sum<G>(dot4(go, v[u]));
             if (DROP) {
               const int src = __shfl_sync(FULL, my_col, (t + u) & 31);
-              da *= keep_scale(drop.seed, uint32_t(i), uint32_t(src), head, drop.threshold, drop.inv_keep);
+              da *= keep_scale(drop.seed, i_id, uint32_t(src), head, drop.threshold, drop.inv_keep);
             }
             fma4(dq, p * (da - delta), k[u]);
           }
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3)
 gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, const int64_t* __restrict__ colptr,
                         const int32_t* __restrict__ row, int64_t n_src, int64_t ldq4, int64_t lddo4, int64_t lddkv4, float scale,
                         DropArgs drop, const float4* __restrict__ dO, const float* __restrict__ stats, float4* __restrict__ dKV,
-                        int packed, int64_t src_base) {
+                        int packed, int64_t src_base, const int32_t* __restrict__ src_ids) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   constexpr int G = 32 / H;
   // the 2H floats of stats ride along as 16-byte (8 for H = 1) cp.async copies issued by the requesting lane and
@@ -299,6 +301,7 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
   const float scale_log2e = scale * LOG2E;
   for (int r = 0; r < cols; ++r) {
     const int64_t j = c0 + r;
+    const uint32_t j_id = DROP ? uint32_t(src_ids ? int64_t(src_ids[j]) : j + src_base) : 0u;
     const int beg = __shfl_sync(FULL, my_rel, r), end = __shfl_sync(FULL, my_rel, r + 1);
     float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
     if (end > beg) {
@@ -334,7 +337,7 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
               float pk = p;
               if (DROP) {
                 const int dst = __shfl_sync(FULL, my_row, (t + u) & 31);
-                const float ks = keep_scale(drop.seed, uint32_t(dst), uint32_t(j + src_base), head, drop.threshold, drop.inv_keep);
+                const float ks = keep_scale(drop.seed, uint32_t(dst), j_id, head, drop.threshold, drop.inv_keep);
                 da *= ks;
                 pk *= ks;
               }
@@ -376,6 +379,32 @@ gat_delta_kernel(const float4* __restrict__ O, const float4* __restrict__ dO, in
   if (lane % G == 0) stats[i * (2 * H) + H + lane / G] = delta;
 }
 
+// Split hub rows: virtual rows [seg_ptr[h], seg_ptr[h+1]) are consecutive slices of hub row hub_rows[h]'s neighbour list,
+// each attended on its own (normalised output O_v, log2-sum-exp lse_v).  The row's softmax over the whole list is
+// O = sum_v O_v 2^(lse_v - lse), lse = log2 sum_v 2^(lse_v), accumulated in ascending v (fixed order).  One warp per hub.
+template <int H>
+__global__ void __launch_bounds__(WARPS * 32)
+gat_merge_segments_kernel(const float4* __restrict__ Oseg, const float* __restrict__ stats_seg, const int64_t* __restrict__ seg_ptr,
+                          const int64_t* __restrict__ hub_rows, int64_t n_hubs, float4* __restrict__ O, float* __restrict__ stats) {
+  constexpr int G = 32 / H;
+  const int lane = lane_id();
+  const int head = lane / G;
+  const int64_t hh = int64_t(blockIdx.x) * WARPS + warp_id();
+  if (hh >= n_hubs) return;
+  const int64_t v0 = seg_ptr[hh], v1 = seg_ptr[hh + 1], i = hub_rows[hh];
+  float m = -INFINITY;
+  for (int64_t v = v0; v < v1; ++v) m = fmaxf(m, stats_seg[v * (2 * H) + head]);
+  float l = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t v = v0; v < v1; ++v) {
+    const float w = exp2f(stats_seg[v * (2 * H) + head] - m);
+    l += w;
+    fma4(acc, w, ldg4(Oseg + v * ROW4 + lane));
+  }
+  O[i * ROW4 + lane] = scale4(acc, 1.f / l);
+  if (lane % G == 0) stats[i * (2 * H) + head] = m + log2f(l);
+}
+
 DropArgs make_drop(float p, uint64_t seed) {
   DropArgs d;
   d.seed = seed;
@@ -411,8 +440,8 @@ constexpr int RU_FWD = 3, RU_DST = 3, RU_SRC = 2;   // edges per arithmetic batc
 using namespace pc;
 
 extern "C" int pc_gat_fwd(const float* q, int64_t ld_q, const float* kv, const int64_t* rowptr, const int32_t* col,
-                          int64_t n_dst, int heads, float dropout_p, uint64_t seed, float* o, float* stats,
-                          pc_stream_t stream) {
+                          int64_t n_dst, int heads, float dropout_p, uint64_t seed, const int32_t* dst_ids, float* o,
+                          float* stats, pc_stream_t stream) {
   if (int rc = check_common(q, rowptr, o, stats, n_dst, heads, dropout_p)) return rc;
   PC_REQUIRE(ld_q >= 128 && ld_q % 4 == 0, PC_ERR_INVALID, "gat_fwd: ld_q=%lld must be a multiple of 4 and >= 128", (long long)ld_q);
   if (n_dst == 0) return PC_OK;
@@ -424,7 +453,7 @@ extern "C" int pc_gat_fwd(const float* q, int64_t ld_q, const float* kv, const i
   if (int rc = ring_smem_attr(gat_fwd_kernel<H, RU_FWD, DROP>, RING_SMEM_KV)) return rc;      \
   gat_fwd_kernel<H, RU_FWD, DROP><<<grid, WARPS * 32, RING_SMEM_KV, st>>>(                    \
       reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(kv), rowptr, col, n_dst, \
-      ld_q / 4, scale_log2e, drop, reinterpret_cast<float4*>(o), stats)
+      ld_q / 4, scale_log2e, drop, dst_ids, reinterpret_cast<float4*>(o), stats)
   if (dropout_p > 0.f) {
     PC_DISPATCH_HEADS(heads, true, CALL_FWD)
   } else {
@@ -436,8 +465,8 @@ extern "C" int pc_gat_fwd(const float* q, int64_t ld_q, const float* kv, const i
 }
 
 extern "C" int pc_gat_bwd_dst(const float* q, int64_t ld_q, const float* kv, const int64_t* rowptr, const int32_t* col,
-                              int64_t n_dst, int heads, float dropout_p, uint64_t seed, const float* o,
-                              const float* d_o, int64_t ld_do, float* stats, float* dq, int64_t ld_dq,
+                              int64_t n_dst, int heads, float dropout_p, uint64_t seed, const int32_t* dst_ids,
+                              const float* o, const float* d_o, int64_t ld_do, float* stats, float* dq, int64_t ld_dq,
                               pc_stream_t stream) {
   if (int rc = check_common(q, rowptr, o, stats, n_dst, heads, dropout_p)) return rc;
   PC_REQUIRE(n_dst == 0 || (d_o && dq), PC_ERR_INVALID, "gat_bwd_dst: null pointer argument");
@@ -453,7 +482,7 @@ extern "C" int pc_gat_bwd_dst(const float* q, int64_t ld_q, const float* kv, con
   gat_bwd_dst_kernel<H, RU_DST, DROP><<<grid, WARPS * 32, RING_SMEM_KV, st>>>(                      \
       reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(kv), rowptr, col, n_dst,       \
       ld_q / 4, ld_do / 4, ld_dq / 4, scale,                                                             \
-      drop, reinterpret_cast<const float4*>(o), reinterpret_cast<const float4*>(d_o), stats,             \
+      drop, dst_ids, reinterpret_cast<const float4*>(o), reinterpret_cast<const float4*>(d_o), stats,    \
       reinterpret_cast<float4*>(dq))
   if (dropout_p > 0.f) {
     PC_DISPATCH_HEADS(heads, true, CALL_BD)
@@ -467,7 +496,8 @@ extern "C" int pc_gat_bwd_dst(const float* q, int64_t ld_q, const float* kv, con
 
 extern "C" int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, const int64_t* colptr, const int32_t* row,
                               int64_t n_src, int heads, float dropout_p, uint64_t seed, const float* d_o, int64_t ld_do,
-                              const float* stats, float* dkv, int64_t ld_dkv, int64_t src_base, pc_stream_t stream) {
+                              const float* stats, float* dkv, int64_t ld_dkv, int64_t src_base, const int32_t* src_ids,
+                              pc_stream_t stream) {
   if (int rc = check_common(kv, colptr, dkv, stats, n_src, heads, dropout_p)) return rc;
   PC_REQUIRE(ld_q >= 128 && ld_q % 4 == 0 && ld_do >= 128 && ld_do % 4 == 0 && ld_dkv >= 256 && ld_dkv % 4 == 0, PC_ERR_INVALID,
              "gat_bwd_src: leading dimensions must be multiples of 4 (q, d_o >= 128, dkv >= 256)");
@@ -484,7 +514,7 @@ extern "C" int pc_gat_bwd_src(const float* q, int64_t ld_q, const float* kv, con
   gat_bwd_src_kernel<H, RU_SRC, DROP><<<grid, WARPS * 32, RING_SMEM_QG, st>>>(                      \
       reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(kv), colptr, row, n_src,       \
       ld_q / 4, ld_do / 4, ld_dkv / 4, scale,                                                            \
-      drop, reinterpret_cast<const float4*>(d_o), stats, reinterpret_cast<float4*>(dkv), packed, src_base)
+      drop, reinterpret_cast<const float4*>(d_o), stats, reinterpret_cast<float4*>(dkv), packed, src_base, src_ids)
   if (dropout_p > 0.f) {
     PC_DISPATCH_HEADS(heads, true, CALL_BS)
   } else {
@@ -508,6 +538,25 @@ extern "C" int pc_gat_delta(const float* o, const float* d_o, int64_t ld_do, int
     case 4: gat_delta_kernel<4><<<grid, WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(o), reinterpret_cast<const float4*>(d_o), ld_do / 4, n, stats); break;
     default: gat_delta_kernel<8><<<grid, WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(o), reinterpret_cast<const float4*>(d_o), ld_do / 4, n, stats); break;
   }
+  PC_LAUNCH_CHECK();
+  return PC_OK;
+}
+
+extern "C" int pc_gat_merge_segments(const float* o_seg, const float* stats_seg, const int64_t* seg_ptr, const int64_t* hub_rows,
+                                     int64_t n_hubs, int heads, float* o, float* stats, pc_stream_t stream) {
+  if (int rc = check_common(o_seg, stats_seg, o, stats, n_hubs, heads, 0.f)) return rc;
+  if (n_hubs == 0) return PC_OK;
+  PC_REQUIRE(seg_ptr && hub_rows, PC_ERR_INVALID, "gat_merge_segments: null pointer");
+  const unsigned grid = unsigned(ceil_div(n_hubs, WARPS));
+  cudaStream_t st = as_stream(stream);
+#define CALL_MERGE(HH) gat_merge_segments_kernel<HH><<<grid, WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(o_seg), stats_seg, seg_ptr, hub_rows, n_hubs, reinterpret_cast<float4*>(o), stats)
+  switch (heads) {
+    case 1: CALL_MERGE(1); break;
+    case 2: CALL_MERGE(2); break;
+    case 4: CALL_MERGE(4); break;
+    default: CALL_MERGE(8); break;
+  }
+#undef CALL_MERGE
   PC_LAUNCH_CHECK();
   return PC_OK;
 }

@@ -67,8 +67,9 @@ class HaloPlan:
         # remap columns: local -> [0, n_local), remote -> n_local + position in `remote`
         is_local = (col >= base) & (col < end)
         ext = torch.where(is_local, col - base, self.n_local + torch.searchsorted(remote, col))
+        # (hub splitting is a single-GPU feature so far: the per-owner column ranges of the backward are not split)
         self.graph = ops.CSRGraph(rowptr.contiguous(), ext.to(torch.int32).contiguous(), self.n_local,
-                                  self.n_local + self.n_halo) if (col.is_cuda and rowptr is not None) else None
+                                  self.n_local + self.n_halo, split_hubs=False) if (col.is_cuda and rowptr is not None) else None
         self.col_ext = ext
         self.rowptr = rowptr
         self.peer: Optional["PeerHalo"] = None

@@ -90,16 +90,74 @@ def set_union(a: torch.Tensor, b: torch.Tensor, num_ids: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- CSR
+HUB_THRESHOLD = 4096   # rows (or transposed columns) with more neighbours than this are split ...
+HUB_SEGMENT = 1024     # ... into virtual rows of this many neighbours (include/pcompanion_b200.h "hub nodes")
+
+
+@dataclass
+class HubSplit:
+    """A CSR whose hub rows were emptied (`ptr`, `idx`) plus a second small CSR over the hubs' neighbour lists cut into
+    virtual rows (`seg_rowptr`, `seg_idx`): virtual rows [seg_ptr[h], seg_ptr[h+1]) are consecutive slices of row
+    hub_rows[h]; seg_row[v] is the real row of virtual row v."""
+    ptr: torch.Tensor          # int64 [n + 1]
+    idx: torch.Tensor          # int32 [E - E_hub]
+    hub_rows: torch.Tensor     # int64 [H]
+    seg_ptr: torch.Tensor      # int64 [H + 1]
+    seg_row: torch.Tensor      # int64 [V]
+    seg_row32: torch.Tensor    # int32 [V]
+    seg_rowptr: torch.Tensor   # int64 [V + 1]
+    seg_idx: torch.Tensor      # int32 [E_hub]
+    seg_ids: torch.Tensor      # int32 [V] = arange(V): pc_rows_segment_sum's column list
+
+    @property
+    def n_virtual(self) -> int:
+        return self.seg_row.numel()
+
+
+def build_hub_split(ptr: torch.Tensor, idx: torch.Tensor, threshold: int, segment: int) -> Optional[HubSplit]:
+    """None when no row has more than `threshold` neighbours (one host read of the maximum degree, once per graph)."""
+    n = ptr.numel() - 1
+    if n <= 0 or idx.numel() == 0:
+        return None
+    deg = ptr[1:] - ptr[:-1]
+    if int(deg.max().item()) <= threshold:
+        return None
+    dev_ = ptr.device
+    is_hub = deg > threshold
+    hub_rows = torch.nonzero(is_hub).squeeze(1)
+    hub_deg = deg[hub_rows]
+    nseg = (hub_deg + segment - 1) // segment
+    seg_ptr = torch.zeros(hub_rows.numel() + 1, dtype=I64, device=dev_)
+    seg_ptr[1:] = torch.cumsum(nseg, 0)
+    seg_row = torch.repeat_interleave(hub_rows, nseg)
+    v = seg_row.numel()
+    k_in_hub = torch.arange(v, device=dev_) - torch.repeat_interleave(seg_ptr[:-1], nseg)
+    seg_len = torch.clamp(torch.repeat_interleave(hub_deg, nseg) - k_in_hub * segment, max=segment)
+    seg_rowptr = torch.zeros(v + 1, dtype=I64, device=dev_)
+    seg_rowptr[1:] = torch.cumsum(seg_len, 0)
+    edge_is_hub = torch.repeat_interleave(is_hub, deg)
+    main_deg = torch.where(is_hub, torch.zeros_like(deg), deg)
+    main_ptr = torch.zeros(n + 1, dtype=I64, device=dev_)
+    main_ptr[1:] = torch.cumsum(main_deg, 0)
+    return HubSplit(main_ptr, idx[~edge_is_hub].contiguous(), hub_rows.contiguous(), seg_ptr, seg_row.contiguous(),
+                    seg_row.to(I32).contiguous(), seg_rowptr, idx[edge_is_hub].contiguous(),
+                    torch.arange(v, dtype=I32, device=dev_))
+
+
 @dataclass
 class CSRGraph:
     """Device CSR of one edge type: row i lists the ascending out-neighbours of node i
     (== sorted(get_neighbors(i, edge_type)), bpg.py:24-31).  The transposed lists (CSC) needed
-    by the deterministic backward are built on first use."""
+    by the deterministic backward are built on first use, and so are the hub splits (rows / transposed columns with more
+    than HUB_THRESHOLD neighbours)."""
     rowptr: torch.Tensor              # int64 [n_rows + 1]
     col: torch.Tensor                 # int32 [E]
     n_rows: int
     n_cols: int
     _t: Optional[Tuple[torch.Tensor, torch.Tensor]] = field(default=None, repr=False)
+    split_hubs: bool = True           # False: never split (regular graphs of the dense drop-in path, halo partitions)
+    _hub: Optional[Tuple] = field(default=None, repr=False)      # (HubSplit | None,) once computed
+    _hub_t: Optional[Tuple] = field(default=None, repr=False)
 
     @property
     def num_edges(self) -> int:
@@ -116,6 +174,21 @@ class CSRGraph:
             colptr, row = csr_from_sorted_keys(keys_t, self.n_cols)
             self._t = (colptr, row)
         return self._t
+
+    def hub_split(self) -> Optional[HubSplit]:
+        if not self.split_hubs:
+            return None
+        if self._hub is None:
+            self._hub = (build_hub_split(self.rowptr, self.col, HUB_THRESHOLD, HUB_SEGMENT),)
+        return self._hub[0]
+
+    def hub_split_t(self) -> Optional[HubSplit]:
+        if not self.split_hubs:
+            return None
+        if self._hub_t is None:
+            colptr, row = self.transposed()
+            self._hub_t = (build_hub_split(colptr, row, HUB_THRESHOLD, HUB_SEGMENT),)
+        return self._hub_t[0]
 
 
 def csr_from_sorted_keys(keys: torch.Tensor, n_rows: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -150,7 +223,7 @@ def regular_graph(batch: int, n_nbr: int, device) -> CSRGraph:
         col = torch.arange(e, dtype=I32, device=device)
         colptr = torch.arange(e + 1, dtype=I64, device=device)
         row = (torch.arange(e, dtype=I64, device=device) // max(n_nbr, 1)).to(I32)
-        g = CSRGraph(rowptr, col, batch, e, (colptr, row))
+        g = CSRGraph(rowptr, col, batch, e, (colptr, row), split_hubs=False)
         if len(_REGULAR_CACHE) > 64:
             _REGULAR_CACHE.clear()
         _REGULAR_CACHE[key] = g
@@ -165,13 +238,28 @@ def _f32_cuda(t: torch.Tensor, what: str):
     return _lib.c_void_p(t.data_ptr())
 
 
+def _gat_fwd_call(q, kv, rowptr, col, n_rows, heads, dropout_p, seed, o, stats, dst_ids=None):
+    call("pc_gat_fwd", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(rowptr, I64, "rowptr"), dev(col, I32, "col"), n_rows,
+         heads, float(dropout_p), int(seed), dev(dst_ids, I32, "dst_ids"), dev(o, F32, "o"), dev(stats, F32, "stats"), stream())
+
+
 def gat_fwd_raw(q: torch.Tensor, kv: torch.Tensor, graph: "CSRGraph", heads: int, dropout_p: float, seed: int):
-    """pc_gat_fwd; q may be a strided [n, 128] view.  Returns (o [n,128], stats [n,2,heads])."""
+    """pc_gat_fwd; q may be a strided [n, 128] view.  Returns (o [n,128], stats [n,2,heads]).  Hub rows are attended slice
+    by slice (virtual rows) and merged (pc_gat_merge_segments)."""
     o = torch.empty(graph.n_rows, EMB, dtype=F32, device=q.device)
     stats = torch.empty(graph.n_rows, 2, heads, dtype=F32, device=q.device)
-    call("pc_gat_fwd", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(graph.rowptr, I64, "rowptr"),
-         dev(graph.col, I32, "col"), graph.n_rows, heads, float(dropout_p), int(seed), dev(o, F32, "o"),
-         dev(stats, F32, "stats"), stream())
+    hs = graph.hub_split()
+    if hs is None:
+        _gat_fwd_call(q, kv, graph.rowptr, graph.col, graph.n_rows, heads, dropout_p, seed, o, stats)
+        return o, stats
+    _gat_fwd_call(q, kv, hs.ptr, hs.idx, graph.n_rows, heads, dropout_p, seed, o, stats)        # hub rows: empty here
+    v = hs.n_virtual
+    qh = q.index_select(0, hs.seg_row).contiguous()
+    oh = torch.empty(v, EMB, dtype=F32, device=q.device)
+    sh = torch.empty(v, 2, heads, dtype=F32, device=q.device)
+    _gat_fwd_call(qh, kv, hs.seg_rowptr, hs.seg_idx, v, heads, dropout_p, seed, oh, sh, hs.seg_row32)
+    call("pc_gat_merge_segments", dev(oh, F32, "o_seg"), dev(sh, F32, "stats_seg"), dev(hs.seg_ptr, I64, "seg_ptr"),
+         dev(hs.hub_rows, I64, "hub_rows"), hs.hub_rows.numel(), heads, dev(o, F32, "o"), dev(stats, F32, "stats"), stream())
     return o, stats
 
 
@@ -179,25 +267,62 @@ def gat_delta_raw(o, d_o, heads, stats) -> None:
     call("pc_gat_delta", dev(o, F32, "o"), _f32_cuda(d_o, "d_o"), d_o.stride(0), o.shape[0], heads, dev(stats, F32, "stats"), stream())
 
 
+def _gat_bwd_dst_call(q, kv, rowptr, col, n_rows, heads, dropout_p, seed, o, d_o, stats, dq, dst_ids=None):
+    call("pc_gat_bwd_dst", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(rowptr, I64, "rowptr"), dev(col, I32, "col"),
+         n_rows, heads, float(dropout_p), int(seed), dev(dst_ids, I32, "dst_ids"), dev(o, F32, "o"), _f32_cuda(d_o, "d_o"),
+         d_o.stride(0), dev(stats, F32, "stats"), _f32_cuda(dq, "dq"), dq.stride(0), stream())
+
+
+def _segment_sums(rows: torch.Tensor, hs: HubSplit) -> torch.Tensor:
+    """[H, W]: per hub, the sum of its virtual rows' partial gradients in ascending slice order."""
+    out = torch.empty(hs.hub_rows.numel(), rows.shape[1], dtype=F32, device=rows.device)
+    call("pc_rows_segment_sum", dev(rows, F32, "rows"), dev(hs.seg_ptr, I64, "rowptr"), dev(hs.seg_ids, I32, "col"),
+         hs.hub_rows.numel(), rows.shape[1], dev(out, F32, "out"), stream())
+    return out
+
+
 def gat_bwd_dst_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, o, d_o, stats, dq) -> None:
-    call("pc_gat_bwd_dst", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(graph.rowptr, I64, "rowptr"),
-         dev(graph.col, I32, "col"), graph.n_rows, heads, float(dropout_p), int(seed), dev(o, F32, "o"),
-         _f32_cuda(d_o, "d_o"), d_o.stride(0), dev(stats, F32, "stats"), _f32_cuda(dq, "dq"), dq.stride(0), stream())
+    hs = graph.hub_split()
+    if hs is None:
+        _gat_bwd_dst_call(q, kv, graph.rowptr, graph.col, graph.n_rows, heads, dropout_p, seed, o, d_o, stats, dq)
+        return
+    _gat_bwd_dst_call(q, kv, hs.ptr, hs.idx, graph.n_rows, heads, dropout_p, seed, o, d_o, stats, dq)   # also writes delta of every row
+    v = hs.n_virtual
+    qh, doh = q.index_select(0, hs.seg_row).contiguous(), d_o.index_select(0, hs.seg_row).contiguous()
+    oh, sh = o.index_select(0, hs.seg_row), stats.index_select(0, hs.seg_row).contiguous()       # the ROW's final O and lse
+    dqh = torch.empty(v, EMB, dtype=F32, device=q.device)
+    _gat_bwd_dst_call(qh, kv, hs.seg_rowptr, hs.seg_idx, v, heads, dropout_p, seed, oh, doh, sh, dqh, hs.seg_row32)
+    dq.index_copy_(0, hs.hub_rows, _segment_sums(dqh, hs))
+
+
+def _gat_bwd_src_call(q, kv, colptr, row, n_cols, heads, dropout_p, seed, d_o, stats, dkv, src_base=0, src_ids=None):
+    call("pc_gat_bwd_src", _f32_cuda(q, "q"), q.stride(0), dev(kv, F32, "kv"), dev(colptr, I64, "colptr"), dev(row, I32, "row"),
+         n_cols, heads, float(dropout_p), int(seed), _f32_cuda(d_o, "d_o"), d_o.stride(0), dev(stats, F32, "stats"),
+         _f32_cuda(dkv, "dkv"), dkv.stride(0), int(src_base), dev(src_ids, I32, "src_ids"), stream())
 
 
 def gat_bwd_src_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, d_o, stats, dkv, col_begin: int = 0,
                     col_count: Optional[int] = None) -> None:
     """needs stats[:,1,:] (delta) from pc_gat_bwd_dst or pc_gat_delta.  (col_begin, col_count) restricts the pass to a
-    range of source columns (rows col_begin.. of kv / dkv)."""
+    range of source columns (rows col_begin.. of kv / dkv); hub columns (whole-graph call only) are split like hub rows."""
     colptr, row = graph.transposed()
+    whole = col_begin == 0 and (col_count is None or col_count == graph.n_cols)
     if col_count is None:
         col_count = graph.n_cols - col_begin
     if col_count <= 0:
         return
-    kv_r, dkv_r = kv[col_begin: col_begin + col_count], dkv[col_begin: col_begin + col_count]
-    call("pc_gat_bwd_src", _f32_cuda(q, "q"), q.stride(0), dev(kv_r, F32, "kv"), dev(colptr[col_begin: col_begin + col_count + 1], I64, "colptr"),
-         dev(row, I32, "row"), col_count, heads, float(dropout_p), int(seed), _f32_cuda(d_o, "d_o"), d_o.stride(0),
-         dev(stats, F32, "stats"), _f32_cuda(dkv_r, "dkv"), dkv_r.stride(0), int(col_begin), stream())
+    hs = graph.hub_split_t() if whole else None
+    if hs is None:
+        kv_r, dkv_r = kv[col_begin: col_begin + col_count], dkv[col_begin: col_begin + col_count]
+        _gat_bwd_src_call(q, kv_r, colptr[col_begin: col_begin + col_count + 1], row, col_count, heads, dropout_p, seed, d_o, stats,
+                          dkv_r, col_begin)
+        return
+    _gat_bwd_src_call(q, kv, hs.ptr, hs.idx, graph.n_cols, heads, dropout_p, seed, d_o, stats, dkv)   # hub columns: zeros
+    v = hs.n_virtual
+    kvh = kv.index_select(0, hs.seg_row).contiguous()
+    dkvh = torch.empty(v, 2 * EMB, dtype=F32, device=q.device)
+    _gat_bwd_src_call(q, kvh, hs.seg_rowptr, hs.seg_idx, v, heads, dropout_p, seed, d_o, stats, dkvh, 0, hs.seg_row32)
+    dkv.index_copy_(0, hs.hub_rows, _segment_sums(dkvh, hs))
 
 
 def gat_bwd_raw(q, kv, graph: "CSRGraph", heads, dropout_p, seed, o, d_o, stats, dq, dkv) -> None:

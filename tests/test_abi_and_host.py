@@ -51,7 +51,7 @@ def test_workspace_queries_need_no_gpu():
 
 def test_argument_errors_are_reported_without_a_gpu():
     from pcompanion_b200 import _lib
-    rc = _lib.LIB.pc_gat_fwd(None, 128, None, None, None, 5, 3, 0.0, 0, None, None, None)
+    rc = _lib.LIB.pc_gat_fwd(None, 128, None, None, None, 5, 3, 0.0, 0, None, None, None, None)
     assert rc != 0 and b"gat" in _lib.LIB.pc_last_error()
     with pytest.raises(RuntimeError, match="native call failed"):
         _lib.check(rc)
