@@ -90,8 +90,13 @@ def set_union(a: torch.Tensor, b: torch.Tensor, num_ids: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- CSR
-HUB_THRESHOLD = 4096   # rows (or transposed columns) with more neighbours than this are split ...
-HUB_SEGMENT = 1024     # ... into virtual rows of this many neighbours (include/pcompanion_b200.h "hub nodes")
+# Rows (or transposed columns) with more neighbours than HUB_THRESHOLD are split into virtual rows of HUB_SEGMENT neighbours
+# (include/pcompanion_b200.h "hub nodes").  A CTA keeps its slot until its slowest warp is done, so even rows of
+# a few hundred neighbours cost occupancy: on the power-law graph of bench.py --workload gat_skewed thresholds of 4096 / 1024
+# left the attention kernels at 8 ms (3.4 ms on a uniform graph of the same size); virtual rows all have the same length,
+# so their launch is perfectly balanced.
+HUB_THRESHOLD = 256
+HUB_SEGMENT = 128
 
 
 @dataclass
