@@ -426,9 +426,16 @@ def gat_partitioned(args, rank, world, dev, nodes_per_gpu=NODES_PER_GPU, edges_p
     del rows, cols
     plan = HaloPlan(rowptr, col_global, bounds, rank)
     plan.graph.transposed()
-    peer_ok = plan.enable_peer_memory()
-    transport = ("pc_halo_push: gather + NVLink stores into the peers' symmetric-memory tables, one launch per direction"
-                 if peer_ok else "NCCL all_to_all_single (" + getattr(plan, "peer_error", "peer memory disabled") + ")")
+    dense_ok = plan.enable_dense_halo()
+    peer_ok = (not dense_ok) and plan.enable_peer_memory()
+    if dense_ok:
+        transport = (f"dense (halo = {plan.halo_fraction():.0%} of the remote rows): h blocks (512 B/row) on the copy engines, one peer "
+                     "per round, K|V projected at the receiver while the next round is in flight; dK|dV blocks returned on the "
+                     "copy engines while the next owner's column range is computed")
+    elif peer_ok:
+        transport = "pc_halo_push: gather + NVLink stores into the peers' symmetric-memory tables, one launch per direction"
+    else:
+        transport = "NCCL all_to_all_single (" + getattr(plan, "peer_error", "peer memory disabled") + ")"
     e_local = col_global.numel()
     x = torch.randn(n_loc, 128, generator=g, device=dev)
     cfg = make_cfg(dev)
@@ -509,6 +516,8 @@ def gat_partitioned(args, rank, world, dev, nodes_per_gpu=NODES_PER_GPU, edges_p
     peak, peak_src = measured_peaks()
     algo = (3152 * e_local + 3676 * n_loc)
     halo_bytes = int(halo_total / world) * 1024
+    if dense_ok:
+        halo_bytes = {"forward_h_blocks": (n_total - n_loc) * 512, "backward_dkv_blocks": (n_total - n_loc) * 1024}
     push_ms = per.get("pc_halo_push")
     return {
         "metric": "gat_edges_per_sec_fwd_bwd", "value": e_total / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,

@@ -26,6 +26,24 @@ import torch.distributed as dist
 from . import ops
 
 
+def _agreed(ok: bool, device, group=None) -> bool:
+    """True iff `ok` on every rank (one all-reduce(MIN)): rank-local failures are turned into a common decision BEFORE the
+    next collective is entered, so that no rank is left waiting in a collective its peers never reach."""
+    flag = torch.full((1,), 1.0 if ok else 0.0, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item() > 0)
+
+
+def _probe_symmetric_memory(device):
+    """Rank-local: None when torch's symmetric memory can allocate here, else the reason."""
+    try:
+        import torch.distributed._symmetric_memory as symm
+        symm.empty(4, dtype=torch.float32, device=device)
+        return None
+    except (ImportError, RuntimeError, AttributeError, NotImplementedError) as e:
+        return f"{type(e).__name__}: {e}"
+
+
 class HaloPlan:
     """Which rows every rank sends / receives, and the CSR remapped to [local | halo] column space.
 
@@ -73,6 +91,8 @@ class HaloPlan:
         self.col_ext = ext
         self.rowptr = rowptr
         self.peer: Optional["PeerHalo"] = None
+        self.dense: Optional["DenseHalo"] = None
+        self.col_global = col_global.to(torch.int32).contiguous() if (col.is_cuda and rowptr is not None) else None
 
     def enable_peer_memory(self, width: int = 256) -> bool:
         """Move the halo rows with pc_halo_push over NVLink peer memory (``PeerHalo``) instead of the NCCL all-to-all.
@@ -83,19 +103,8 @@ class HaloPlan:
         # Every collective below is reached by every rank: rank-local failures (import, capability, allocation) only
         # set a flag, and the outcome is agreed on with an all-reduce(MIN) BEFORE the next collective is entered.
         dev = self.send_idx.device
-
-        def agreed(ok: bool) -> bool:
-            flag = torch.full((1,), 1.0 if ok else 0.0, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-            return bool(flag.item() > 0)
-
-        try:
-            import torch.distributed._symmetric_memory as symm
-            symm.empty(4, dtype=torch.float32, device=dev)             # rank-local probe: the allocator works here
-            err = None
-        except (ImportError, RuntimeError, AttributeError, NotImplementedError) as e:
-            err = f"{type(e).__name__}: {e}"
-        if not agreed(err is None):
+        err = _probe_symmetric_memory(dev)
+        if not _agreed(err is None, dev, self.group):
             self.peer_error = err or "symmetric memory unavailable on a peer rank"
             return False
         peer = PeerHalo.__new__(PeerHalo)
@@ -105,11 +114,42 @@ class HaloPlan:
             err = None
         except (RuntimeError, MemoryError) as e:
             err = f"{type(e).__name__}: {e}"
-        if not agreed(err is None):
+        if not _agreed(err is None, dev, self.group):
             self.peer_error = err or "symmetric allocation failed on a peer rank"
             return False
         peer._rendezvous()                                             # collective (exchange of the peer mappings)
         self.peer = peer
+        return True
+
+    def halo_fraction(self) -> float:
+        """Share of the OTHER ranks' rows this rank needs as halo rows."""
+        remote = self.bounds[-1] - self.n_local
+        return self.n_halo / remote if remote > 0 else 0.0
+
+    def enable_dense_halo(self, min_fraction: float = 0.5) -> bool:
+        """Dense exchange (``DenseHalo``) for graphs whose partitions need most of every peer's rows: whole row blocks travel
+        as contiguous copy-engine copies and the K|V projection of remote rows runs at the receiver.  Collective.  Returns
+        False (transport unchanged) when some rank's halo is sparser than `min_fraction`, or symmetric memory is unavailable."""
+        if self.world == 1 or not self.send_idx.is_cuda or self.rowptr is None or os.environ.get("PC_HALO_TRANSPORT", "") in ("nccl", "push"):
+            return False
+        dev = self.send_idx.device
+        err = _probe_symmetric_memory(dev)
+        if err is None and self.halo_fraction() < min_fraction:
+            err = f"halo fraction {self.halo_fraction():.2f} < {min_fraction}"
+        if not _agreed(err is None, dev, self.group):
+            self.dense_error = err or "dense halo not applicable on a peer rank"
+            return False
+        dense = DenseHalo.__new__(DenseHalo)
+        try:
+            dense._allocate(self)                                      # rank-local
+            err = None
+        except (RuntimeError, MemoryError) as e:
+            err = f"{type(e).__name__}: {e}"
+        if not _agreed(err is None, dev, self.group):
+            self.dense_error = err or "symmetric allocation failed on a peer rank"
+            return False
+        dense._rendezvous()                                            # collective
+        self.dense = dense
         return True
 
     @staticmethod
@@ -268,6 +308,82 @@ class PeerHalo:
         index = NULL does the same from the SMs: measured 9 -> 4.6 ms of wgrad slowdown at 4 GPUs, so not used here.)"""
         for owner, _, _ in self.reverse_runs():
             self.push_reverse_run(dkv_ext, owner)
+
+
+class DenseHalo:
+    """Halo exchange for partitions that need (almost) every remote row - a uniform random graph at 2-8 GPUs needs
+    92-100 % of them, so gathering "the rows the peer asked for" buys nothing and costs an SM kernel.
+
+    Forward: every rank copies its block of FFN outputs h [n_local, 128] (512 B per row - half of a K|V row) into every
+    peer's table with the COPY ENGINES, one peer per round, a cross-rank barrier after each round; the receiver
+    projects K|V for a peer's block as soon as that round has landed, while the next round is in flight, so the SMs
+    never wait for more than one round.  Columns keep their GLOBAL ids (the table has a row for every node), hence no
+    index lists and the same neighbour order as on one GPU.
+    Backward: the src-major pass runs one column range per owner; each range of dK|dV partials leaves for its owner's
+    return buffer on the copy engines while the next range is computed; the owner adds the returned blocks in rank
+    order in one pass (pc_rows_reduce_peers).  Weight gradients need nothing else: dW_kv = dKV_total^T h on the owner."""
+
+    def _allocate(self, plan: "HaloPlan") -> None:
+        import torch.distributed._symmetric_memory as symm
+        self.plan = plan
+        self._group = plan.group if plan.group is not None else dist.group.WORLD
+        dev = plan.send_idx.device
+        self.n_total = plan.bounds[-1]
+        self.n_loc_max = max(plan.bounds[q + 1] - plan.bounds[q] for q in range(plan.world))
+        self._h = symm.empty(self.n_total * 128, dtype=torch.float32, device=dev)
+        self._ret = symm.empty(plan.world * self.n_loc_max * 256, dtype=torch.float32, device=dev)
+
+    def _rendezvous(self) -> None:
+        import torch.distributed._symmetric_memory as symm
+        plan = self.plan
+        world, rank, dev = plan.world, plan.rank, plan.send_idx.device
+        hh = symm.rendezvous(self._h, self._group.group_name)
+        hr = symm.rendezvous(self._ret, self._group.group_name)
+        self._handles = (hh, hr)
+        self.h_all = self._h.view(self.n_total, 128)
+        self.ret_rows = self._ret.view(world * self.n_loc_max, 256)
+        self._h_peer = [hh.get_buffer(p, (self.n_total, 128), torch.float32) if p != rank else None for p in range(world)]
+        self._ret_peer = [hr.get_buffer(p, (world, self.n_loc_max, 256), torch.float32) if p != rank else None for p in range(world)]
+        self.kv_all = torch.empty(self.n_total, 256, dtype=torch.float32, device=dev)
+        self.graph = ops.CSRGraph(plan.rowptr.contiguous(), plan.col_global, plan.n_local, self.n_total, split_hubs=False)
+        self.graph.transposed()
+        slot = torch.arange(plan.n_local, dtype=torch.int32, device=dev).unsqueeze(0) + \
+            (torch.arange(world, dtype=torch.int32, device=dev) * self.n_loc_max).unsqueeze(1)
+        slot[rank] = -1
+        self.slot = slot.contiguous()
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.side = torch.cuda.Stream(device=dev)
+        self.events = [torch.cuda.Event() for _ in range(world)]
+        self.version = 0
+
+    def barrier(self) -> None:
+        dist.all_reduce(self._flag, group=self._group)
+
+    def block(self, q: int):
+        return self.plan.bounds[q], self.plan.bounds[q + 1]
+
+    def h_local(self) -> torch.Tensor:
+        b0, b1 = self.block(self.plan.rank)
+        return self.h_all[b0:b1]
+
+    def exchange_h(self) -> None:
+        """Round k: my h block -> rank (r + k)'s table; barrier; event k.  Issued on the side stream, after everything that
+        is on the current stream now."""
+        plan = self.plan
+        world, rank = plan.world, plan.rank
+        b0, b1 = self.block(rank)
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            self.barrier()                                           # every rank is done reading last step's remote blocks
+            for k in range(1, world):
+                self._h_peer[(rank + k) % world][b0:b1].copy_(self.h_all[b0:b1])
+                self.barrier()                                       # round k has landed everywhere
+                self.events[k].record(self.side)
+
+    def return_block(self, dkv_all: torch.Tensor, owner: int) -> None:
+        """dK|dV partials of `owner`'s columns -> slot `rank` of its return buffer (copy engines, current stream)."""
+        b0, b1 = self.block(owner)
+        self._ret_peer[owner][self.plan.rank, : b1 - b0].copy_(dkv_all[b0:b1])
 
 
 class _HaloGather(torch.autograd.Function):

@@ -42,7 +42,7 @@ def _allreduce_sums(sums: torch.Tensor, count: int, group, sync: bool, total: Op
 
 
 def ffn_forward_core(x, w0, b0, gamma, beta, w3, b3, w5, b5, training, eps, momentum, run_mean, run_var, num_batches,
-                     group=None, sync_bn=False, total=None):
+                     group=None, sync_bn=False, total=None, h_out=None):
     """Linear -> BatchNorm1d -> Tanh -> Linear -> Tanh -> Linear (product2vec.py:14-21) on [rows, 128] with the C-ABI kernels:
     tcgen05 projections (tanh in the epilogue), float64 fixed-order column statistics, one BN-apply + tanh pass.
     Returns (z1, a1, a2, h, mean, rstd, count); running statistics are updated in place with nn.BatchNorm1d's rule
@@ -69,7 +69,7 @@ def ffn_forward_core(x, w0, b0, gamma, beta, w3, b3, w5, b5, training, eps, mome
     shift = (beta.double() - mean64 * gamma.double() * rstd64).to(F32)
     a1 = ops.scale_shift_tanh(z1, scale, shift, tanh=True)
     a2 = ops.linear_tc(a1, w3, b3, ops.EPI_BIAS_TANH)
-    h = ops.linear_tc(a2, w5, b5)
+    h = ops.linear_tc(a2, w5, b5, out0=h_out)
     return z1, a1, a2, h, mean, rstd, count
 
 
@@ -149,17 +149,35 @@ class _P2VGraphLayer(torch.autograd.Function):
         x = x.contiguous()
         n = x.shape[0]
         total = plan.bounds[-1] - plan.bounds[0] if plan is not None else None
+        dense = plan.dense if plan is not None else None
         z1, a1, a2, h, mean, rstd, count = ffn_forward_core(x, w0, b0, gamma, beta, w3, b3, w5, b5, training, eps, momentum,
-                                                            run_mean, run_var, cfg.get("num_batches_tracked"), group, sync_bn, total)
+                                                            run_mean, run_var, cfg.get("num_batches_tracked"), group, sync_bn, total,
+                                                            h_out=dense.h_local() if dense is not None else None)
         qg = torch.empty(n, 256, dtype=F32, device=x.device)
         n_ext = graph.n_cols
-        peer = plan.peer if plan is not None else None
-        kv = peer.table(n_ext) if peer is not None else torch.empty(n_ext, 256, dtype=F32, device=x.device)
-        if plan is None:
+        peer = plan.peer if (plan is not None and dense is None) else None
+        if dense is not None:
+            # h blocks travel on the copy engines, one peer per round; K|V of a remote block is projected HERE as soon as its
+            # round has landed, while the next round is in flight (DenseHalo)
+            graph = dense.graph
+            kv = dense.kv_all
+            dense.version += 1
+            dense.exchange_h()
+            w_kv, b_kv = w_in[128:].contiguous(), b_in[128:].contiguous()
+            b0_, b1_ = dense.block(plan.rank)
+            ops.linear_tc(h, w_kv, b_kv, out0=kv[b0_:b1_])
+            ops.linear_tc(h, w_in[:128], b_in[:128], out0=qg[:, :128])
+            for k in range(1, plan.world):
+                s0, s1 = dense.block((plan.rank - k) % plan.world)
+                torch.cuda.current_stream().wait_event(dense.events[k])
+                ops.linear_tc(dense.h_all[s0:s1], w_kv, b_kv, out0=kv[s0:s1])
+        elif plan is None:
+            kv = torch.empty(n_ext, 256, dtype=F32, device=x.device)
             ops.linear_tc(h, w_in, b_in, split=128, out0=qg[:, :128], out1=kv[:n])
         elif peer is not None:
             # K|V straight into the symmetric table; one kernel gathers the rows the peers need and stores them into
             # the peers' tables over NVLink while Q is projected
+            kv = peer.table(n_ext)
             ops.linear_tc(h, w_in[128:], b_in[128:], out0=kv[:n])
             peer.barrier()                                   # every rank is done reading its previous halo rows
             peer.push_forward(kv[:n])
@@ -167,6 +185,7 @@ class _P2VGraphLayer(torch.autograd.Function):
             peer.barrier()                                   # all pushes have landed
         else:
             # K|V first, start the halo all-to-all, project Q while the rows travel
+            kv = torch.empty(n_ext, 256, dtype=F32, device=x.device)
             ops.linear_tc(h, w_in[128:], b_in[128:], out0=kv[:n])
             work = plan.forward_exchange(ops.rows_gather(kv[:n], plan.send_idx), kv[n:], async_op=True)
             ops.linear_tc(h, w_in[:128], b_in[:128], out0=qg[:, :128])
@@ -175,7 +194,8 @@ class _P2VGraphLayer(torch.autograd.Function):
         o, stats = ops.gat_fwd_raw(qg[:, :128], kv, graph, heads, p_drop, seed)
         emb = ops.linear_tc(o, w_o, b_o, ops.EPI_BIAS_SELECT, aux=h, rowptr=graph.rowptr)
         ctx.save_for_backward(x, z1, a1, a2, h, qg, kv, o, stats, mean, rstd, gamma, w0, w3, w5, w_in, w_o)
-        ctx.cfg = dict(cfg, count=count, kv_version=peer.version if peer is not None else 0)
+        ctx.cfg = dict(cfg, graph=graph, count=count,
+                       kv_version=dense.version if dense is not None else (peer.version if peer is not None else 0))
         return emb
 
     @staticmethod
@@ -202,16 +222,35 @@ class _P2VGraphLayer(torch.autograd.Function):
             dq = torch.empty(n, 128, dtype=F32, device=x.device)
             dkv = torch.empty(graph.n_cols, 256, dtype=F32, device=x.device)
             ops.gat_delta_raw(o, qg[:, 128:], heads, stats)
-            peer = plan.peer
+            dense = plan.dense
+            peer = plan.peer if dense is None else None
             src_args = (qg[:, :128], kv, graph, heads, p_drop, seed, qg[:, 128:], stats, dkv)
-            if peer is not None:
+            stale = "p2v_graph_layer.backward: the K|V table of this HaloPlan was overwritten by a later forward; run backward before the next forward"
+            main = torch.cuda.current_stream()
+            lo = 0                                                     # first local row of dkv
+            if dense is not None:
+                if dense.version != cfg["kv_version"]:
+                    raise RuntimeError(stale)
+                # one column range per owner; a range's partials leave for the owner's return buffer on the copy engines
+                # (side stream) while the next range is computed, the local range and the dst-major pass follow
+                for k in range(1, plan.world):
+                    owner = (plan.rank + k) % plan.world
+                    c0, c1 = dense.block(owner)
+                    ops.gat_bwd_src_raw(*src_args, col_begin=c0, col_count=c1 - c0)
+                    dense.side.wait_stream(main)
+                    with torch.cuda.stream(dense.side):
+                        dense.return_block(dkv, owner)
+                with torch.cuda.stream(dense.side):
+                    dense.barrier()
+                lo = dense.block(plan.rank)[0]
+                ops.gat_bwd_src_raw(*src_args, col_begin=lo, col_count=n)
+                returned, slot, work = dense.ret_rows, dense.slot, None
+            elif peer is not None:
                 if peer.version != cfg["kv_version"]:
-                    raise RuntimeError("p2v_graph_layer.backward: the symmetric K|V table was overwritten by a later forward "
-                                       "on the same HaloPlan; run backward before the next forward")
+                    raise RuntimeError(stale)
                 # halo columns first, ONE RANGE PER OWNER (each owner's columns are contiguous): a range's partials start
                 # travelling to their owner on the copy engines (side stream) while the next range is computed; the
                 # local columns and the dst-major pass follow, so the whole return path hides behind ~10 ms of compute
-                main = torch.cuda.current_stream()
                 for owner, c0, cnt in peer.reverse_runs():
                     ops.gat_bwd_src_raw(*src_args, col_begin=c0, col_count=cnt)
                     peer.side.wait_stream(main)
@@ -220,24 +259,28 @@ class _P2VGraphLayer(torch.autograd.Function):
                 with torch.cuda.stream(peer.side):
                     peer.barrier()
                 ops.gat_bwd_src_raw(*src_args, col_begin=0, col_count=n)
-                returned, work = peer.returned(), None
+                returned, slot, work = peer.returned(), plan.slot, None
             else:
                 ops.gat_bwd_src_raw(*src_args, col_begin=n)               # halo columns, then their all-to-all ...
                 returned = torch.empty(plan.send_idx.numel(), 256, dtype=F32, device=x.device)
                 work = plan.reverse_exchange(dkv[n:], returned, async_op=True)
                 ops.gat_bwd_src_raw(*src_args, col_begin=0, col_count=n)  # ... travels while the local columns are computed
+                slot = plan.slot
+            dkv_loc = dkv[lo: lo + n]
             ops.gat_bwd_dst_raw(qg[:, :128], kv, graph, heads, p_drop, seed, o, qg[:, 128:], stats, dq)
             dw_q, db_q = ops.wgrad_tc(dq, h)
             w_in_t = w_in.t().contiguous()                                            # [128, 384]
             d_h = ops.linear_tc(dq, w_in_t[:, :128].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_rest)
             if work is not None:
                 work.wait()
-            if peer is not None:
-                torch.cuda.current_stream().wait_stream(peer.side)
-            ops.rows_reduce_peers_(dkv[:n], returned, plan.slot)      # one pass, fixed peer order: deterministic
-            dw_kv, db_kv = ops.wgrad_tc(dkv[:n], h)
+            if dense is not None:
+                main.wait_stream(dense.side)
+            elif peer is not None:
+                main.wait_stream(peer.side)
+            ops.rows_reduce_peers_(dkv_loc, returned, slot)           # one pass, fixed peer order: deterministic
+            dw_kv, db_kv = ops.wgrad_tc(dkv_loc, h)
             dw_in, db_in = torch.cat([dw_q, dw_kv]), torch.cat([db_q, db_kv])
-            d_h = ops.linear_tc(dkv[:n], w_in_t[:, 128:].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_h)
+            d_h = ops.linear_tc(dkv_loc, w_in_t[:, 128:].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_h)
         dx, dw0, db0, d_gamma, d_beta, dw3, db3, dw5, db5 = ffn_backward_core(
             d_h, x, z1, a1, a2, mean, rstd, gamma, w0, w3, w5, training, count, group, sync_bn, ctx.needs_input_grad[0])
         return (dx, dw0, db0, d_gamma, d_beta, dw3, db3, dw5, db5, dw_in, db_in, dw_o, db_o, None)

@@ -66,9 +66,9 @@ def check_partitioned(rank: int, world: int, dev: torch.device, n: int = 3000, r
     report["csr_build"] = "bit-exact"
     plan = HaloPlan(lp, lc, bounds, rank)
 
-    def run(m):
+    def run(m, plan_=None):
         m.zero_grad()
-        o = forward_graph_partitioned(m, torch.tensor(x[b0:b1], device=dev), plan)
+        o = forward_graph_partitioned(m, torch.tensor(x[b0:b1], device=dev), plan_ if plan_ is not None else plan)
         (o * torch.tensor(w[b0:b1], device=dev)).sum().backward()
         allreduce_gradients(m)
         return o
@@ -105,6 +105,19 @@ def check_partitioned(rank: int, world: int, dev: torch.device, n: int = 3000, r
     elif world > 1:
         transport += f" only ({getattr(plan, 'peer_error', 'peer memory disabled')})"
     report["halo_transport"] = transport
+    # dense exchange (h blocks on the copy engines, K|V projected at the receiver, columns keep their global ids)
+    if world > 1:
+        plan_d = HaloPlan(lp, lc, bounds, rank)
+        if plan_d.enable_dense_halo(min_fraction=0.0):
+            for _ in range(2):                               # twice: the symmetric buffers are reused across steps
+                out_d = run(model2, plan_d)
+            ge_d = grad_errs(model2, ref_grads)
+            report["dense_halo"] = {"forward_rel_err": rel_err(out_d, out_full[b0:b1]), "grad_rel_err_max": max(ge_d.values()),
+                                    "halo_fraction": plan_d.halo_fraction()}
+            require(report["dense_halo"]["forward_rel_err"] <= rel, f"dense-halo forward differs: {report['dense_halo']}")
+            require(report["dense_halo"]["grad_rel_err_max"] <= rel, f"dense-halo gradient differs: {ge_d}")
+        else:
+            report["dense_halo"] = "unavailable: " + getattr(plan_d, "dense_error", "?")
 
     # triplet loss whose positives / negatives live on any rank: rows fetched from their owners, gradients returned
     trips = [np.concatenate([np.random.default_rng(20 + r).integers(bounds[r], bounds[r + 1], (64, 1)),
