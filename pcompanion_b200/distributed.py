@@ -315,9 +315,9 @@ class DenseHalo:
     92-100 % of them, so gathering "the rows the peer asked for" buys nothing and costs an SM kernel.
 
     Forward: every rank copies its block of FFN outputs h [n_local, 128] (512 B per row - half of a K|V row) into every
-    peer's table with the COPY ENGINES, one peer per round, a cross-rank barrier after each round; the receiver
-    projects K|V for a peer's block as soon as that round has landed, while the next round is in flight, so the SMs
-    never wait for more than one round.  Columns keep their GLOBAL ids (the table has a row for every node), hence no
+    peer's table with the COPY ENGINES, one peer per round, each copy followed by a point-to-point "landed" signal; the
+    receiver projects K|V for a peer's block as soon as that block has landed, while the next one is in flight, so the
+    SMs never wait for more than one round.  Columns keep their GLOBAL ids (the table has a row for every node), hence no
     index lists and the same neighbour order as on one GPU.
     Backward: the src-major pass runs one column range per owner; each range of dK|dV partials leaves for its owner's
     return buffer on the copy engines while the next range is computed; the owner adds the returned blocks in rank
@@ -351,13 +351,15 @@ class DenseHalo:
             (torch.arange(world, dtype=torch.int32, device=dev) * self.n_loc_max).unsqueeze(1)
         slot[rank] = -1
         self.slot = slot.contiguous()
-        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
         self.side = torch.cuda.Stream(device=dev)
-        self.events = [torch.cuda.Event() for _ in range(world)]
         self.version = 0
 
-    def barrier(self) -> None:
-        dist.all_reduce(self._flag, group=self._group)
+    # Cross-rank ordering uses the point-to-point signals of torch's symmetric memory (one-thread kernels that flip a flag in
+    # the peer's signal pad) instead of NCCL barriers: a NCCL kernel cannot co-reside with the persistent GEMM CTAs (they
+    # hold ~213 KB of shared memory per SM), so a barrier issued on the side stream only ran in the gaps between GEMMs and
+    # delayed every round by up to one GEMM (measured at 2 GPUs: 25.7 ms per step with barriers against 25.0 ms for the push transport).
+    SIGNAL_TIMEOUT_MS = 30_000         # a lost peer becomes a CUDA error, not a hung GPU
+    CH_LANDED, CH_CONSUMED = 0, 1
 
     def block(self, q: int):
         return self.plan.bounds[q], self.plan.bounds[q + 1]
@@ -367,23 +369,41 @@ class DenseHalo:
         return self.h_all[b0:b1]
 
     def exchange_h(self) -> None:
-        """Round k: my h block -> rank (r + k)'s table; barrier; event k.  Issued on the side stream, after everything that
-        is on the current stream now."""
+        """Round k: my h block -> rank (r + k)'s table, then a "landed" signal to that rank.  Before overwriting a peer's copy
+        of my block the peer's "consumed" signal of the previous forward is awaited.  Issued on the side stream, after
+        everything that is on the current stream now."""
         plan = self.plan
         world, rank = plan.world, plan.rank
         b0, b1 = self.block(rank)
+        hh = self._handles[0]
         self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
-            self.barrier()                                           # every rank is done reading last step's remote blocks
             for k in range(1, world):
-                self._h_peer[(rank + k) % world][b0:b1].copy_(self.h_all[b0:b1])
-                self.barrier()                                       # round k has landed everywhere
-                self.events[k].record(self.side)
+                p = (rank + k) % world
+                if self.version > 1:
+                    hh.wait_signal(p, self.CH_CONSUMED, self.SIGNAL_TIMEOUT_MS)
+                self._h_peer[p][b0:b1].copy_(self.h_all[b0:b1])
+                hh.put_signal(p, self.CH_LANDED, self.SIGNAL_TIMEOUT_MS)
+
+    def wait_block(self, src: int) -> None:
+        """Current stream: rank `src`'s h block of this forward has landed in my table."""
+        self._handles[0].wait_signal(src, self.CH_LANDED, self.SIGNAL_TIMEOUT_MS)
+
+    def release_block(self, src: int) -> None:
+        """Current stream: I am done reading rank `src`'s h block (it may be overwritten by src's next forward)."""
+        self._handles[0].put_signal(src, self.CH_CONSUMED, self.SIGNAL_TIMEOUT_MS)
 
     def return_block(self, dkv_all: torch.Tensor, owner: int) -> None:
-        """dK|dV partials of `owner`'s columns -> slot `rank` of its return buffer (copy engines, current stream)."""
+        """dK|dV partials of `owner`'s columns -> slot `rank` of its return buffer (copy engines), then a "landed" signal."""
         b0, b1 = self.block(owner)
         self._ret_peer[owner][self.plan.rank, : b1 - b0].copy_(dkv_all[b0:b1])
+        self._handles[1].put_signal(owner, self.CH_LANDED, self.SIGNAL_TIMEOUT_MS)
+
+    def wait_returned(self) -> None:
+        """Current stream: every peer's block of partials for my columns has landed in my return buffer."""
+        for p in range(self.plan.world):
+            if p != self.plan.rank:
+                self._handles[1].wait_signal(p, self.CH_LANDED, self.SIGNAL_TIMEOUT_MS)
 
 
 class _HaloGather(torch.autograd.Function):

@@ -168,9 +168,11 @@ class _P2VGraphLayer(torch.autograd.Function):
             ops.linear_tc(h, w_kv, b_kv, out0=kv[b0_:b1_])
             ops.linear_tc(h, w_in[:128], b_in[:128], out0=qg[:, :128])
             for k in range(1, plan.world):
-                s0, s1 = dense.block((plan.rank - k) % plan.world)
-                torch.cuda.current_stream().wait_event(dense.events[k])
+                src = (plan.rank - k) % plan.world                # round k: the block of rank r - k arrives here
+                s0, s1 = dense.block(src)
+                dense.wait_block(src)
                 ops.linear_tc(dense.h_all[s0:s1], w_kv, b_kv, out0=kv[s0:s1])
+                dense.release_block(src)
         elif plan is None:
             kv = torch.empty(n_ext, 256, dtype=F32, device=x.device)
             ops.linear_tc(h, w_in, b_in, split=128, out0=qg[:, :128], out1=kv[:n])
@@ -240,8 +242,6 @@ class _P2VGraphLayer(torch.autograd.Function):
                     dense.side.wait_stream(main)
                     with torch.cuda.stream(dense.side):
                         dense.return_block(dkv, owner)
-                with torch.cuda.stream(dense.side):
-                    dense.barrier()
                 lo = dense.block(plan.rank)[0]
                 ops.gat_bwd_src_raw(*src_args, col_begin=lo, col_count=n)
                 returned, slot, work = dense.ret_rows, dense.slot, None
@@ -274,7 +274,8 @@ class _P2VGraphLayer(torch.autograd.Function):
             if work is not None:
                 work.wait()
             if dense is not None:
-                main.wait_stream(dense.side)
+                main.wait_stream(dense.side)                          # my own sends are done reading dkv
+                dense.wait_returned()                                 # every peer's block for my columns has landed
             elif peer is not None:
                 main.wait_stream(peer.side)
             ops.rows_reduce_peers_(dkv_loc, returned, slot)           # one pass, fixed peer order: deterministic
