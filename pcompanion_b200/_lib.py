@@ -122,6 +122,27 @@ def call(name: str, *args) -> None:
     PROFILE.append((name, start, end))
 
 
+class region:
+    """with region("wait:h_block"): ...  - when bench.py's per-call profiling is on, the enclosed stream work (waits on
+    other streams / peers) is timed like a native call; otherwise free."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            PROFILE.append((self.name, self.start, end))
+        return False
+
+
 def stream() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 

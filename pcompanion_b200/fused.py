@@ -23,6 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from ._lib import region
 
 F32 = torch.float32
 
@@ -170,7 +171,8 @@ class _P2VGraphLayer(torch.autograd.Function):
             for k in range(1, plan.world):
                 src = (plan.rank - k) % plan.world                # round k: the block of rank r - k arrives here
                 s0, s1 = dense.block(src)
-                dense.wait_block(src)
+                with region("wait:h_block"):
+                    dense.wait_block(src)
                 ops.linear_tc(dense.h_all[s0:s1], w_kv, b_kv, out0=kv[s0:s1])
                 dense.release_block(src)
         elif plan is None:
@@ -274,10 +276,12 @@ class _P2VGraphLayer(torch.autograd.Function):
             if work is not None:
                 work.wait()
             if dense is not None:
-                main.wait_stream(dense.side)                          # my own sends are done reading dkv
-                dense.wait_returned()                                 # every peer's block for my columns has landed
+                with region("wait:returned_blocks"):
+                    main.wait_stream(dense.side)                      # my own sends are done reading dkv
+                    dense.wait_returned()                             # every peer's block for my columns has landed
             elif peer is not None:
-                main.wait_stream(peer.side)
+                with region("wait:returned_runs"):
+                    main.wait_stream(peer.side)
             ops.rows_reduce_peers_(dkv_loc, returned, slot)           # one pass, fixed peer order: deterministic
             dw_kv, db_kv = ops.wgrad_tc(dkv_loc, h)
             dw_in, db_in = torch.cat([dw_q, dw_kv]), torch.cat([db_q, db_kv])
