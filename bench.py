@@ -505,6 +505,10 @@ def gat_partitioned(args, rank, world, dev, nodes_per_gpu=NODES_PER_GPU, edges_p
     for name, s0, s1 in prof:
         per[name] = per.get(name, 0.0) + s0.elapsed_time(s1) / 2
     abi_ms = {k: round(v, 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
+    # timeline of the second profiled step on rank 0: start offset and duration of every native call / copy-engine copy /
+    # cross-rank wait, in issue order (calls on the side stream overlap the ones on the main stream)
+    last = prof[len(prof) // 2:]
+    timeline = [[name, round(last[0][1].elapsed_time(s0), 3), round(s0.elapsed_time(s1), 3)] for name, s0, s1 in last]
     for _ in range(2):
         step_e2e()
     e2e_ms, _ = timed_steps(step_e2e, args.steps, dev, world)
@@ -542,6 +546,7 @@ def gat_partitioned(args, rank, world, dev, nodes_per_gpu=NODES_PER_GPU, edges_p
                      "note": "whole step per GPU against the sparse-kernel algorithmic bytes (3152 B/edge + 3676 B/node); "
                              "the halo exchange moves halo_bytes over NVLink each way on top"},
         "abi_ms_per_step": abi_ms, "abi_total_ms_per_step": round(sum(abi_ms.values()), 3),
+        "timeline_rank0": {"columns": ["call", "start_ms", "duration_ms"], "rows": timeline},
         "clocks": clocks,
         "e2e": {"value": e_total / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": (x_host.numel() * 4 + trip_host.numel() * 8) * world, "d2h_bytes_per_step": 4 * world},

@@ -24,6 +24,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from ._lib import region
 
 
 def _agreed(ok: bool, device, group=None) -> bool:
@@ -300,7 +301,8 @@ class PeerHalo:
         """One owner's run of halo partials -> its return buffer, as a plain peer copy on the copy engines (current stream)."""
         src0, cnt, view = self._r_copy[owner]
         if cnt:
-            view.copy_(dkv_ext[src0: src0 + cnt])
+            with region("ce:return_run"):
+                view.copy_(dkv_ext[src0: src0 + cnt])
 
     def push_reverse(self, dkv_ext: torch.Tensor) -> None:
         """Every owner's run of halo partials is contiguous on both sides, so it travels as a plain peer copy on the
@@ -353,6 +355,9 @@ class DenseHalo:
         self.slot = slot.contiguous()
         self.side = torch.cuda.Stream(device=dev)
         self.version = 0
+        npad = 2 * world
+        self._pads = [[h.get_signal_pad(p, (npad,), torch.int32) if p != rank else None for p in range(world)] for h in (hh, hr)]
+        self._one = torch.ones(1, dtype=torch.int32, device=dev)
 
     # Cross-rank ordering uses the point-to-point signals of torch's symmetric memory (one-thread kernels that flip a flag in
     # the peer's signal pad) instead of NCCL barriers: a NCCL kernel cannot co-reside with the persistent GEMM CTAs (they
@@ -368,22 +373,30 @@ class DenseHalo:
         b0, b1 = self.block(self.plan.rank)
         return self.h_all[b0:b1]
 
+    def _flag(self, handle_idx: int, peer: int, channel: int) -> None:
+        """Raise signal (channel, from me) in `peer`'s pad with a 4-byte copy-engine copy: the side stream never launches a
+        kernel (a one-thread put_signal kernel there queued up behind the compute kernels of the main stream)."""
+        off = self.plan.world * channel + self.plan.rank
+        self._pads[handle_idx][peer][off: off + 1].copy_(self._one)
+
     def exchange_h(self) -> None:
-        """Round k: my h block -> rank (r + k)'s table, then a "landed" signal to that rank.  Before overwriting a peer's copy
-        of my block the peer's "consumed" signal of the previous forward is awaited.  Issued on the side stream, after
-        everything that is on the current stream now."""
+        """Round k: my h block -> rank (r + k)'s table, then a "landed" flag in that rank's signal pad.  Before overwriting a
+        peer's copy of my block the peer's "consumed" signal of the previous forward is awaited (current stream).  The
+        copies are issued on the side stream, after everything that is on the current stream now."""
         plan = self.plan
         world, rank = plan.world, plan.rank
         b0, b1 = self.block(rank)
         hh = self._handles[0]
+        if self.version > 1:
+            for k in range(1, world):
+                hh.wait_signal((rank + k) % world, self.CH_CONSUMED, self.SIGNAL_TIMEOUT_MS)
         self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
             for k in range(1, world):
                 p = (rank + k) % world
-                if self.version > 1:
-                    hh.wait_signal(p, self.CH_CONSUMED, self.SIGNAL_TIMEOUT_MS)
-                self._h_peer[p][b0:b1].copy_(self.h_all[b0:b1])
-                hh.put_signal(p, self.CH_LANDED, self.SIGNAL_TIMEOUT_MS)
+                with region("ce:h_block"):
+                    self._h_peer[p][b0:b1].copy_(self.h_all[b0:b1])
+                    self._flag(0, p, self.CH_LANDED)
 
     def wait_block(self, src: int) -> None:
         """Current stream: rank `src`'s h block of this forward has landed in my table."""
@@ -394,10 +407,11 @@ class DenseHalo:
         self._handles[0].put_signal(src, self.CH_CONSUMED, self.SIGNAL_TIMEOUT_MS)
 
     def return_block(self, dkv_all: torch.Tensor, owner: int) -> None:
-        """dK|dV partials of `owner`'s columns -> slot `rank` of its return buffer (copy engines), then a "landed" signal."""
+        """dK|dV partials of `owner`'s columns -> slot `rank` of its return buffer (copy engines), then a "landed" flag."""
         b0, b1 = self.block(owner)
-        self._ret_peer[owner][self.plan.rank, : b1 - b0].copy_(dkv_all[b0:b1])
-        self._handles[1].put_signal(owner, self.CH_LANDED, self.SIGNAL_TIMEOUT_MS)
+        with region("ce:return_block"):
+            self._ret_peer[owner][self.plan.rank, : b1 - b0].copy_(dkv_all[b0:b1])
+            self._flag(1, owner, self.CH_LANDED)
 
     def wait_returned(self) -> None:
         """Current stream: every peer's block of partials for my columns has landed in my return buffer."""
