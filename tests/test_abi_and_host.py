@@ -151,3 +151,46 @@ def test_similarity_dataset_requires_pairs_like_reference():
     b.similarity_pairs = []
     with pytest.raises(ValueError, match="No similarity pairs found in BPG"):
         SimilarityDataset(b, make_cfg())
+
+
+REF_CKPT = "/root/reference/models/run_20241206_210422/product2vec.pth"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CKPT), reason="the reference checkout (with its shipped checkpoints) is not on this box")
+def test_shipped_reference_checkpoint_loads_into_the_drop_in_modules():
+    """scripts/pretrain_product2vec.py:44-49 layout {'model_state_dict', 'embeddings', 'type_to_idx'}: the state_dict loads
+    strictly into Product2Vec, the embedding dict feeds PCompanion.__init__ as train.py:42-43 does."""
+    from pcompanion_b200 import PCompanion, Product2Vec
+    ck = torch.load(REF_CKPT, map_location="cpu", weights_only=True)
+    m = Product2Vec(make_cfg())
+    missing = m.load_state_dict(ck["model_state_dict"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, ck["model_state_dict"][k]), k
+    emb = ck["embeddings"]
+    pcm = PCompanion(make_cfg(), emb)
+    ids = list(emb.keys())
+    assert pcm.product_embeddings.weight.shape == (len(ids), 128) and not pcm.product_embeddings.weight.requires_grad
+    assert pcm.product_to_idx[ids[0]] == 0 and pcm.product_to_idx[ids[-1]] == len(ids) - 1
+    assert torch.equal(pcm.product_embeddings.weight[7], emb[ids[7]].float())
+
+
+def test_scalable_generator_chain_equals_the_oracle_chain_on_shared_uniforms():
+    """pcompanion_b200.synthetic.edge_chain (torch, O(E)) against oracle.bpg.edge_chain (numpy restatement of
+    synthetic_data.py:101-128) on the same candidate pairs and the same uniforms: identical edge lists per type."""
+    from oracle import bpg as obpg
+    from pcompanion_b200.synthetic import edge_chain
+    rng = np.random.default_rng(0)
+    n, pairs = 5000, 200_000
+    category = rng.integers(0, 5, n).astype(np.int32)
+    a, b = rng.integers(0, n, pairs), rng.integers(0, n, pairs)
+    keep = a != b
+    src, dst = np.minimum(a, b)[keep].astype(np.int32), np.maximum(a, b)[keep].astype(np.int32)
+    u = rng.random((3, src.size)).astype(np.float32)
+    ours = edge_chain(torch.tensor(category), torch.tensor(src), torch.tensor(dst), torch.tensor(u[0]), torch.tensor(u[1]), torch.tensor(u[2]))
+    ref = obpg.edge_chain(n, category, src, dst, u[0], u[1], u[2])
+    for t in ("co_view", "purchase_after_view", "co_purchase"):
+        s, d = ours[t]
+        keys = (s.numpy().astype(np.int64) << 32) | d.numpy().astype(np.int64)
+        assert np.array_equal(keys, np.asarray(ref[t]).astype(np.int64)), t
+    assert 0.30 < ours["co_view"][0].numel() / src.size < 0.36          # 0.3 (x1.5 inside a category, 1/5 of the pairs)
