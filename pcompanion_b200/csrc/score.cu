@@ -44,7 +44,13 @@ constexpr int SC_ACC = 4;                           // TMEM accumulator buffers 
 constexpr int KP = 8;                               // candidates kept per (row, unit, chunk) list
 constexpr int SC_MAX_K = 16;                        // largest k (a row has at least 4 lists)
 constexpr int SC_LIST_BYTES = BM * SC_CHUNKS * KP * 8;   // candidate lists (score, index) of the 512 epilogue threads
-constexpr int SC_SMEM = SC_OPERAND_BYTES + SC_LIST_BYTES + 1024 + 4096;
+// Type filter: per lane quarter (32 rows) a table bucket -> bit mask of the rows whose type falls into the bucket.  With ~1 K
+// types a [32 rows x 32 products] chunk holds about one (row, product) pair of equal type, so instead of reading all 32 x 32
+// scores from TMEM and building the mask with 32 shuffles per tile, a warp looks up which rows could want each product
+// (one shared-memory load per lane), and fetches ONE TMEM column per surviving product.
+constexpr int SC_BUCKETS = 768;
+constexpr int SC_FILTER_BYTES = 4 * SC_BUCKETS * 4;      // 12 KB
+constexpr int SC_SMEM = SC_OPERAND_BYTES + SC_LIST_BYTES + SC_FILTER_BYTES + 1024 + 4096;
 
 struct ScoreParams {
   int64_t rows, products;
@@ -65,7 +71,8 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* list_s = reinterpret_cast<float*>(smem + SC_OPERAND_BYTES);                                  // [128][4][KP] scores
   int32_t* list_i = reinterpret_cast<int32_t*>(smem + SC_OPERAND_BYTES + BM * SC_CHUNKS * KP * 4);    // [128][4][KP] indices
-  uint8_t* misc = smem + SC_OPERAND_BYTES + SC_LIST_BYTES;
+  uint32_t* filter = reinterpret_cast<uint32_t*>(smem + SC_OPERAND_BYTES + SC_LIST_BYTES);             // [4 quarters][SC_BUCKETS]
+  uint8_t* misc = smem + SC_OPERAND_BYTES + SC_LIST_BYTES + SC_FILTER_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // q_full, q_empty, b_full[8], b_empty[8], tfull[4], tempty[4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
   const uint32_t q_full = smem_u32(bars + 0), q_empty = smem_u32(bars + 1);
@@ -183,6 +190,32 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       for (int j = 0; j < KP; ++j) { my_s[j] = -INFINITY; my_i[j] = -1; }
       float thr = -INFINITY;          // weakest kept score once the list is full
       int kept = 0;
+      // insert (y, product index) keeping (score desc, index asc): indices arrive ascending, so an equal score goes after
+      auto insert = [&](float y, int32_t pidx) {
+        if (kept < KP || y > thr) {                 // thr follows every insertion
+          int pos = kept < KP ? kept : KP - 1;
+          while (pos > 0 && my_s[pos - 1] < y) {
+            my_s[pos] = my_s[pos - 1];
+            my_i[pos] = my_i[pos - 1];
+            --pos;
+          }
+          my_s[pos] = y;
+          my_i[pos] = pidx;
+          if (kept < KP) ++kept;
+          if (kept == KP) thr = my_s[KP - 1];
+        }
+      };
+      // the type filter of this unit's rows; shared by the four chunk warps of a lane quarter (named barrier 1 + quad).  Used
+      // when every row of the quarter is restricted to a type; unrestricted rows take the scan-everything path below.
+      uint32_t* my_filter = filter + quad * SC_BUCKETS;
+      const bool filtered = p.type_id != nullptr && p.row_type != nullptr && !__any_sync(FULL, row_ok && rt < 0);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");      // every warp of the quarter is done with the previous unit's table
+      if (chunk == 0) {
+        for (int b = lane; b < SC_BUCKETS; b += 32) my_filter[b] = 0u;
+        __syncwarp();
+        if (row_ok && rt >= 0) atomicOr(&my_filter[uint32_t(rt) % SC_BUCKETS], 1u << lane);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
       auto type_of = [&](int64_t tile) -> int {   // lane j holds the type of product j of the warp's chunk of that tile
         const int64_t pidx = tile * SC_BN + c0 + lane;
         return (tile < t_end && pidx < p.products) ? (p.type_id ? p.type_id[pidx] : 0) : -2;   // -2: past the catalog end
@@ -192,37 +225,37 @@ score_topk_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int64_t n0 = nt * SC_BN;
         const int t_lane = t_next;
         t_next = type_of(nt + 1);      // in flight while this tile is processed; the warps never synchronise with each other
-        mbar_wait(tfull_bar + 8 * ra.stage, ra.phase);
-        tc_fence_after();
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(ra.stage * SC_BN + c0), r);
-        // bit j of mask: product j of the chunk is eligible for my row (exists and has my row's type)
-        const uint32_t valid = __ballot_sync(FULL, t_lane != -2);
-        uint32_t mask = 0;
-        if (__any_sync(FULL, rt >= 0)) {
+        if (filtered) {
+          // rows of my quarter that could want product `lane` (bucket collisions are resolved by the exact compare below)
+          const uint32_t want = t_lane >= 0 ? my_filter[uint32_t(t_lane) % SC_BUCKETS] : 0u;
+          uint32_t cand = __ballot_sync(FULL, want != 0u);
+          mbar_wait(tfull_bar + 8 * ra.stage, ra.phase);
+          tc_fence_after();
+          while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int tj = __shfl_sync(FULL, t_lane, j);
+            uint32_t y1;
+            tmem_ld1(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(ra.stage * SC_BN + c0 + j), y1);   // warp-uniform column
+            if (row_ok && rt == tj) insert(__uint_as_float(y1), int32_t(n0 + c0 + j));
+          }
+        } else {
+          mbar_wait(tfull_bar + 8 * ra.stage, ra.phase);
+          tc_fence_after();
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(ra.stage * SC_BN + c0), r);
+          // bit j of mask: product j of the chunk is eligible for my row (exists and has my row's type)
+          const uint32_t valid = __ballot_sync(FULL, t_lane != -2);
+          uint32_t mask = 0;
+          if (__any_sync(FULL, rt >= 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mask |= uint32_t(__shfl_sync(FULL, t_lane, j) == rt) << j;   // rt >= 0 never equals -2
-        }
-        if (rt < 0) mask = valid;
-        if (row_ok && mask) {
+            for (int j = 0; j < 32; ++j) mask |= uint32_t(__shfl_sync(FULL, t_lane, j) == rt) << j;   // rt >= 0 never equals -2
+          }
+          if (rt < 0) mask = valid;
+          if (row_ok && mask) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (mask & (1u << j)) {
-              const float y = __uint_as_float(r[j]);
-              if (kept < KP || y > thr) {               // thr follows every insertion
-                // insert keeping (score desc, index asc): indices arrive ascending, so an equal score goes after
-                int pos = kept < KP ? kept : KP - 1;
-                while (pos > 0 && my_s[pos - 1] < y) {
-                  my_s[pos] = my_s[pos - 1];
-                  my_i[pos] = my_i[pos - 1];
-                  --pos;
-                }
-                my_s[pos] = y;
-                my_i[pos] = int32_t(n0 + c0 + j);
-                if (kept < KP) ++kept;
-                if (kept == KP) thr = my_s[KP - 1];
-              }
-            }
+            for (int j = 0; j < 32; ++j)
+              if (mask & (1u << j)) insert(__uint_as_float(r[j]), int32_t(n0 + c0 + j));
           }
         }
         tc_fence_before();
