@@ -134,7 +134,9 @@ int pc_gat_merge_segments(const float* o_seg, const float* stats_seg, const int6
  * Q | K|V outputs of the packed in-projection.  epilogue: 0 bias, 1 tanh(. + bias),
  * 2 (. + bias) * (1 - aux^2) (gradient through tanh, aux = tanh output),
  * 3 row r keeps (. + bias) if rowptr[r+1] > rowptr[r] else takes aux[r, :] (product2vec.py:76),
- * 4 (. + bias) + aux. */
+ * 4 (. + bias) + aux,
+ * 5 row r keeps (. + bias) if rowptr[r+1] > rowptr[r] else 0 (backward of that select: no masked copy of the gradient),
+ * 6 (. + bias), plus aux[r, :] on the rows WITHOUT neighbours (their gradient bypasses the attention). */
 size_t pc_linear_workspace_bytes(int n, int k);   /* holds the weight pre-split into tf32 hi | lo */
 int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, const float* bias,
                      int epilogue, const float* aux, int64_t ld_aux, const int64_t* rowptr, float* out0, int64_t ld0,
@@ -156,6 +158,11 @@ int pc_wgrad_tf32x3(const float* dy, int64_t m, int n, int64_t ld_dy, const floa
 size_t pc_col_reduce_workspace_bytes(int n);
 int pc_col_stats(const float* x, int64_t m, int n, int64_t ldx, double* sums, void* workspace, size_t workspace_bytes,
                  pc_stream_t stream);
+/* sums[0, c] = sum of x[r, c] over the rows r with neighbours (rowptr[r+1] > rowptr[r]), sums[1, :] = 0: the out-projection's
+ * bias gradient under the "rows without neighbours keep ffn(x)" select of product2vec.py:76, without materialising the
+ * masked gradient.  Same fixed-order float64 reduction and workspace as pc_col_stats. */
+int pc_col_sum_selected(const float* x, int64_t m, int n, int64_t ldx, const int64_t* rowptr, double* sums, void* workspace,
+                        size_t workspace_bytes, pc_stream_t stream);
 int pc_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* x, int64_t ldx, int64_t m, int n, const float* mean,
                      const float* rstd, double* sums, void* workspace, size_t workspace_bytes, pc_stream_t stream);
 int pc_scale_shift_tanh(const float* x, int64_t ldx, int64_t m, int n, const float* scale, const float* shift,

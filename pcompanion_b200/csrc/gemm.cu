@@ -51,7 +51,9 @@ constexpr int SPLIT_THREADS = 256;      // warps 8-15
 constexpr int SMEM_MISC = 4096;         // barriers, tmem pointer, bias
 constexpr int GEMM_SMEM = OPERAND_BYTES + 1024 + SMEM_MISC;
 
-enum Epilogue { EPI_BIAS = 0, EPI_BIAS_TANH = 1, EPI_TANH_GRAD = 2, EPI_BIAS_SELECT = 3, EPI_BIAS_ADD = 4 };
+enum Epilogue { EPI_BIAS = 0, EPI_BIAS_TANH = 1, EPI_TANH_GRAD = 2, EPI_BIAS_SELECT = 3, EPI_BIAS_ADD = 4,
+                EPI_ROWMASK = 5,          // rows without neighbours (rowptr) give 0: backward of the row select, no mask pass
+                EPI_ADD_UNSELECTED = 6 }; // rows without neighbours add their aux row (they kept ffn(x) in the forward)
 
 struct LinearParams {
   int64_t m;
@@ -61,7 +63,7 @@ struct LinearParams {
   float* out0; int ld0; int split;   // columns [0, split) -> out0
   float* out1; int ld1;              // columns [split, n) -> out1 (may be null when split == n)
   int epilogue;
-  const float* aux; int ld_aux;      // EPI_TANH_GRAD: tanh output t (y = acc * (1 - t^2)); EPI_BIAS_SELECT: fallback rows
+  const float* aux; int ld_aux;      // EPI_TANH_GRAD: tanh output t (y = acc * (1 - t^2)); EPI_BIAS_SELECT / ADD_UNSELECTED: rows without neighbours
   const int64_t* rowptr;             // EPI_BIAS_SELECT: row keeps acc + bias iff rowptr[r+1] > rowptr[r]
   // TOPK instantiation (pc_type_scores_topk): a CTA owns a CONTIGUOUS run of tiles (m-tile major), every epilogue thread
   // keeps the best tk_k columns of its row over the run and flushes them to list (segment, set) of the row
@@ -277,7 +279,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // place and the tile goes out again as the result.  The rows of the NEXT tile are pulled into L2 a tile ahead.
     // The row-select epilogue only needs aux for rows without neighbours and keeps plain loads.
     const bool aux_tile = p.epilogue == EPI_TANH_GRAD || p.epilogue == EPI_BIAS_ADD;
-    const bool has_aux = aux_tile || p.epilogue == EPI_BIAS_SELECT;
+    const bool row_aux = p.epilogue == EPI_BIAS_SELECT || p.epilogue == EPI_ADD_UNSELECTED;   // aux only for rows without neighbours
+    const bool has_aux = aux_tile || row_aux;
     uint32_t aux_phase = 0;
     // TOPK: best tk_k (score, column) of my row over this CTA's run of tiles; columns arrive ascending, so the strict
     // comparison keeps the lower column on ties
@@ -304,7 +307,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     auto prefetch_aux = [&](int64_t tile) {
       if (!has_aux || tile >= tiles) return;
       const int64_t prow = (tile / p.n_tiles) * BM + trow;
-      if (prow < p.m && (p.epilogue != EPI_BIAS_SELECT || p.rowptr[prow + 1] == p.rowptr[prow]))   // select reads aux only for empty rows
+      if (prow < p.m && (!row_aux || p.rowptr[prow + 1] == p.rowptr[prow]))   // select reads aux only for empty rows
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.aux + prow * p.ld_aux + (tile % p.n_tiles) * p.bn),
                      "r"(uint32_t(p.bn) * 4u)
                      : "memory");
@@ -323,7 +326,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       bool keep = true;
-      if (p.epilogue == EPI_BIAS_SELECT && row < p.m) keep = p.rowptr[row + 1] > p.rowptr[row];
+      if ((row_aux || p.epilogue == EPI_ROWMASK) && row < p.m) keep = p.rowptr[row + 1] > p.rowptr[row];
       for (int c0 = set * 32; c0 < p.bn; c0 += 64) {
         if (aux_tile && issuer) {   // the staging tile is free once the previous store has read it
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -382,13 +385,18 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               y[4 * j] += a.x; y[4 * j + 1] += a.y; y[4 * j + 2] += a.z; y[4 * j + 3] += a.w;
             }
           }
-        } else if (p.epilogue == EPI_BIAS_SELECT && !keep && row < p.m) {
+        } else if (row_aux && !keep && row < p.m) {
           const float* aux = p.aux + row * p.ld_aux + n;
+          const bool add = p.epilogue == EPI_ADD_UNSELECTED;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 a = *reinterpret_cast<const float4*>(aux + j);
-            y[j] = a.x; y[j + 1] = a.y; y[j + 2] = a.z; y[j + 3] = a.w;
+            y[j] = (add ? y[j] : 0.f) + a.x; y[j + 1] = (add ? y[j + 1] : 0.f) + a.y;
+            y[j + 2] = (add ? y[j + 2] : 0.f) + a.z; y[j + 3] = (add ? y[j + 3] : 0.f) + a.w;
           }
+        } else if (p.epilogue == EPI_ROWMASK && !keep) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = 0.f;
         }
         if (!aux_tile) {
           // the previous chunk's bulk store must have finished reading the staging tile
@@ -702,10 +710,12 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   PC_REQUIRE(lda % 4 == 0 && ld0 % 4 == 0 && (split == n || ld1 % 4 == 0), PC_ERR_INVALID, "linear: leading dimensions must be multiples of 4 floats");
   PC_REQUIRE((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out0) | reinterpret_cast<uintptr_t>(out1)) % 16 == 0, PC_ERR_INVALID,
              "linear: A / outputs must be 16-byte aligned (TMA)");
-  PC_REQUIRE(epilogue >= EPI_BIAS && epilogue <= EPI_BIAS_ADD, PC_ERR_INVALID, "linear: unknown epilogue %d", epilogue);
-  PC_REQUIRE((epilogue != EPI_TANH_GRAD && epilogue != EPI_BIAS_SELECT && epilogue != EPI_BIAS_ADD) || (aux && ld_aux % 4 == 0),
+  PC_REQUIRE(epilogue >= EPI_BIAS && epilogue <= EPI_ADD_UNSELECTED, PC_ERR_INVALID, "linear: unknown epilogue %d", epilogue);
+  PC_REQUIRE((epilogue != EPI_TANH_GRAD && epilogue != EPI_BIAS_SELECT && epilogue != EPI_BIAS_ADD && epilogue != EPI_ADD_UNSELECTED) ||
+                 (aux && ld_aux % 4 == 0),
              PC_ERR_INVALID, "linear: epilogue needs aux");
-  PC_REQUIRE(epilogue != EPI_BIAS_SELECT || rowptr, PC_ERR_INVALID, "linear: select epilogue needs rowptr");
+  PC_REQUIRE((epilogue != EPI_BIAS_SELECT && epilogue != EPI_ROWMASK && epilogue != EPI_ADD_UNSELECTED) || rowptr, PC_ERR_INVALID,
+             "linear: row-select epilogues need rowptr");
   PC_REQUIRE(workspace_bytes >= pc_linear_workspace_bytes(n, k), PC_ERR_WORKSPACE, "linear: workspace too small");
   LinearParams p;
   p.m = m; p.n = n; p.k = k;

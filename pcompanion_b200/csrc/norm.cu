@@ -16,10 +16,12 @@ constexpr int RED_THREADS = 256;
 
 // sums[0, c] = sum_r f0(r, c), sums[1, c] = sum_r f1(r, c) over rows, n4 = n / 4 column groups.
 // MODE 0: f0 = x, f1 = x^2.   MODE 1: f0 = dy, f1 = dy * (x - mean) * rstd.
+// MODE 2: f0 = x on rows with neighbours (rowptr[r+1] > rowptr[r]), 0 elsewhere; f1 = 0  (bias gradient of the row select).
 template <int MODE>
 __global__ void __launch_bounds__(RED_THREADS)
 col_reduce_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb, int64_t m, int n4,
-                  const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ partial) {
+                  const float* __restrict__ mean, const float* __restrict__ rstd, const int64_t* __restrict__ rowptr,
+                  double* __restrict__ partial) {
   extern __shared__ double sm[];  // [row_lanes][2][n4 * 4]
   const int row_lanes = RED_THREADS / n4;
   const int cg = threadIdx.x % n4, rl = threadIdx.x / n4;
@@ -34,8 +36,11 @@ col_reduce_kernel(const float* __restrict__ a, int64_t lda, const float* __restr
     const int64_t r_beg = int64_t(blockIdx.x) * rows_per_cta;
     const int64_t r_end = min(m, r_beg + rows_per_cta);
     for (int64_t r = r_beg + rl; r < r_end; r += row_lanes) {
+      if (MODE == 2 && rowptr[r + 1] <= rowptr[r]) continue;
       const float4 x = ld_stream4(reinterpret_cast<const float4*>(a + r * lda) + cg);
-      if (MODE == 0) {
+      if (MODE == 2) {
+        s0[0] += x.x; s0[1] += x.y; s0[2] += x.z; s0[3] += x.w;
+      } else if (MODE == 0) {
         s0[0] += x.x; s0[1] += x.y; s0[2] += x.z; s0[3] += x.w;
         s1[0] += double(x.x) * x.x; s1[1] += double(x.y) * x.y; s1[2] += double(x.z) * x.z; s1[3] += double(x.w) * x.w;
       } else {
@@ -136,7 +141,7 @@ int elementwise_grid(int64_t total) {
 
 template <int MODE>
 int col_reduce(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int n, const float* mean,
-               const float* rstd, double* sums, void* ws, size_t ws_bytes, cudaStream_t st) {
+               const float* rstd, const int64_t* rowptr, double* sums, void* ws, size_t ws_bytes, cudaStream_t st) {
   PC_REQUIRE(m > 0 && n >= 4 && n % 4 == 0 && n <= 1024 && RED_THREADS % (n / 4) == 0, PC_ERR_UNSUPPORTED,
              "col_reduce: n=%d must divide 1024 and be a multiple of 4", n);
   PC_REQUIRE(a && sums && ws && lda % 4 == 0 && ldb % 4 == 0, PC_ERR_INVALID, "col_reduce: bad pointer / leading dimension");
@@ -144,7 +149,7 @@ int col_reduce(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t
   PC_REQUIRE(ws_bytes >= size_t(grid) * 2 * n * sizeof(double), PC_ERR_WORKSPACE, "col_reduce: workspace too small");
   const int n4 = n / 4, row_lanes = RED_THREADS / n4;
   const size_t smem = size_t(row_lanes) * 2 * n * sizeof(double);
-  col_reduce_kernel<MODE><<<grid, RED_THREADS, smem, st>>>(a, lda, b, ldb, m, n4, mean, rstd, reinterpret_cast<double*>(ws));
+  col_reduce_kernel<MODE><<<grid, RED_THREADS, smem, st>>>(a, lda, b, ldb, m, n4, mean, rstd, rowptr, reinterpret_cast<double*>(ws));
   PC_LAUNCH_CHECK();
   col_reduce_final_kernel<<<(2 * n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double*>(ws), grid, 2 * n, sums);
   PC_LAUNCH_CHECK();
@@ -160,14 +165,20 @@ extern "C" size_t pc_col_reduce_workspace_bytes(int n) { return size_t(sm_count(
 
 extern "C" int pc_col_stats(const float* x, int64_t m, int n, int64_t ldx, double* sums, void* workspace,
                             size_t workspace_bytes, pc_stream_t stream) {
-  return col_reduce<0>(x, ldx, nullptr, 4, m, n, nullptr, nullptr, sums, workspace, workspace_bytes, as_stream(stream));
+  return col_reduce<0>(x, ldx, nullptr, 4, m, n, nullptr, nullptr, nullptr, sums, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int pc_col_sum_selected(const float* x, int64_t m, int n, int64_t ldx, const int64_t* rowptr, double* sums, void* workspace,
+                                   size_t workspace_bytes, pc_stream_t stream) {
+  PC_REQUIRE(rowptr, PC_ERR_INVALID, "col_sum_selected: null rowptr");
+  return col_reduce<2>(x, ldx, nullptr, 4, m, n, nullptr, nullptr, rowptr, sums, workspace, workspace_bytes, as_stream(stream));
 }
 
 extern "C" int pc_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* x, int64_t ldx, int64_t m, int n,
                                 const float* mean, const float* rstd, double* sums, void* workspace,
                                 size_t workspace_bytes, pc_stream_t stream) {
   PC_REQUIRE(x && mean && rstd, PC_ERR_INVALID, "bn_bwd_reduce: null pointer");
-  return col_reduce<1>(dy, ld_dy, x, ldx, m, n, mean, rstd, sums, workspace, workspace_bytes, as_stream(stream));
+  return col_reduce<1>(dy, ld_dy, x, ldx, m, n, mean, rstd, nullptr, sums, workspace, workspace_bytes, as_stream(stream));
 }
 
 extern "C" int pc_scale_shift_tanh(const float* x, int64_t ldx, int64_t m, int n, const float* scale, const float* shift,

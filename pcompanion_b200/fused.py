@@ -210,16 +210,20 @@ class _P2VGraphLayer(torch.autograd.Function):
         heads, p_drop, seed, training = cfg["heads"], cfg["dropout_p"], cfg["seed"], cfg["training"]
         group, sync_bn, count = cfg.get("group"), cfg.get("sync_bn", False), cfg["count"]
         n = x.shape[0]
-        d_out, d_rest = ops.mask_split(d_emb, graph.rowptr)
+        # rows without neighbours kept ffn(x) in the forward (product2vec.py:76): their gradient bypasses the attention.
+        # No masked copies of d_emb: the dO GEMM zeroes those rows in its epilogue, dW_o needs no mask (their O rows are
+        # zero), the bias gradient is a selected column sum, and the d_h GEMM adds d_emb back on exactly those rows.
+        d_emb = d_emb.contiguous()
         # out-projection
-        ops.linear_tc(d_out, w_o.t().contiguous(), None, out0=qg[:, 128:])            # dO next to Q
-        dw_o, db_o = ops.wgrad_tc(d_out, o)
+        ops.linear_tc(d_emb, w_o.t().contiguous(), None, ops.EPI_ROWMASK, rowptr=graph.rowptr, out0=qg[:, 128:])   # dO next to Q
+        dw_o, _ = ops.wgrad_tc(d_emb, o, want_bias=False)
+        db_o = ops.col_sum_selected(d_emb, graph.rowptr).to(F32)
         # attention
         if plan is None:
             dqkv = torch.empty(n, 384, dtype=F32, device=x.device)
             ops.gat_bwd_raw(qg[:, :128], kv, graph, heads, p_drop, seed, o, qg[:, 128:], stats, dqkv[:, :128], dqkv[:, 128:])
             dw_in, db_in = ops.wgrad_tc(dqkv, h)
-            d_h = ops.linear_tc(dqkv, w_in.t().contiguous(), None, ops.EPI_BIAS_ADD, aux=d_rest)
+            d_h = ops.linear_tc(dqkv, w_in.t().contiguous(), None, ops.EPI_ADD_UNSELECTED, aux=d_emb, rowptr=graph.rowptr)
         else:
             # src-major pass first: its halo rows start travelling back to their owners while the dst-major
             # pass and the Q-side GEMMs run (the all-to-all is asynchronous on NCCL's stream)
@@ -272,7 +276,7 @@ class _P2VGraphLayer(torch.autograd.Function):
             ops.gat_bwd_dst_raw(qg[:, :128], kv, graph, heads, p_drop, seed, o, qg[:, 128:], stats, dq)
             dw_q, db_q = ops.wgrad_tc(dq, h)
             w_in_t = w_in.t().contiguous()                                            # [128, 384]
-            d_h = ops.linear_tc(dq, w_in_t[:, :128].contiguous(), None, ops.EPI_BIAS_ADD, aux=d_rest)
+            d_h = ops.linear_tc(dq, w_in_t[:, :128].contiguous(), None, ops.EPI_ADD_UNSELECTED, aux=d_emb, rowptr=graph.rowptr)
             if work is not None:
                 work.wait()
             if dense is not None:

@@ -367,7 +367,7 @@ def gat_attention(q: torch.Tensor, kv: torch.Tensor, graph: CSRGraph, heads: int
 
 
 # --------------------------------------------------------------------------- dense projections (tcgen05)
-EPI_BIAS, EPI_BIAS_TANH, EPI_TANH_GRAD, EPI_BIAS_SELECT, EPI_BIAS_ADD = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_TANH, EPI_TANH_GRAD, EPI_BIAS_SELECT, EPI_BIAS_ADD, EPI_ROWMASK, EPI_ADD_UNSELECTED = 0, 1, 2, 3, 4, 5, 6
 
 
 def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
@@ -422,6 +422,16 @@ def col_stats(x: torch.Tensor) -> torch.Tensor:
     call("pc_col_stats", _f32_cuda(x, "x"), m, n, x.stride(0), dev(sums, F64, "sums"), dev(ws, torch.uint8, "ws"),
          ws.numel(), stream())
     return sums
+
+
+def col_sum_selected(x: torch.Tensor, rowptr: torch.Tensor) -> torch.Tensor:
+    """float64 [n]: column sums of x over the rows that have neighbours (rowptr[r+1] > rowptr[r])."""
+    m, n = x.shape
+    sums = torch.empty(2, n, dtype=F64, device=x.device)
+    ws = _col_reduce_ws(n, x.device)
+    call("pc_col_sum_selected", _f32_cuda(x, "x"), m, n, x.stride(0), dev(rowptr, I64, "rowptr"), dev(sums, F64, "sums"),
+         dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    return sums[0]
 
 
 def bn_bwd_reduce(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor) -> torch.Tensor:
