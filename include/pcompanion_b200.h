@@ -136,11 +136,15 @@ int pc_gat_merge_segments(const float* o_seg, const float* stats_seg, const int6
  * 3 row r keeps (. + bias) if rowptr[r+1] > rowptr[r] else takes aux[r, :] (product2vec.py:76),
  * 4 (. + bias) + aux,
  * 5 row r keeps (. + bias) if rowptr[r+1] > rowptr[r] else 0 (backward of that select: no masked copy of the gradient),
- * 6 (. + bias), plus aux[r, :] on the rows WITHOUT neighbours (their gradient bypasses the attention). */
+ * 6 (. + bias), plus aux[r, :] on the rows WITHOUT neighbours (their gradient bypasses the attention).
+ * col_sums (float64 [2, n], may be NULL; epilogue 0 and n <= 256 only): column sums of Y and of Y^2 over the m rows, taken
+ * from the output tiles while they are still in shared memory (the BatchNorm statistics of product2vec.py:16 without
+ * a pass over Y); per-CTA float64 partials summed in CTA order, bit-reproducible. */
 size_t pc_linear_workspace_bytes(int n, int k);   /* holds the weight pre-split into tf32 hi | lo */
 int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, const float* bias,
                      int epilogue, const float* aux, int64_t ld_aux, const int64_t* rowptr, float* out0, int64_t ld0,
-                     int split, float* out1, int64_t ld1, void* workspace, size_t workspace_bytes, pc_stream_t stream);
+                     int split, float* out1, int64_t ld1, double* col_sums, void* workspace, size_t workspace_bytes,
+                     pc_stream_t stream);
 
 /* Weight / bias gradient of such a projection (autograd's AddmmBackward for the weight):
  *   dW[n, k] = sum_m dY[m, n] X[m, k],  db[n] = sum_m dY[m, n]  (db may be NULL)

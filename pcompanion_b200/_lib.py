@@ -43,7 +43,7 @@ PROTOTYPES = {
     "pc_affine2": (c_int, [P, c_int64, P, c_int64, c_int64, c_int, P, P, P, P, c_int64, P]),
     "pc_mask_split": (c_int, [P, c_int64, c_int, P, P, P, P]),
     "pc_linear_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "pc_linear_tf32x3": (c_int, [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int64, P, P, c_int64, c_int, P, c_int64, P, c_size_t, P]),
+    "pc_linear_tf32x3": (c_int, [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int64, P, P, c_int64, c_int, P, c_int64, P, P, c_size_t, P]),
     "pc_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pc_wgrad_tf32x3": (c_int, [P, c_int64, c_int, c_int64, P, c_int, c_int64, P, P, P, c_size_t, P]),
     "pc_type_scores_topk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),

@@ -49,7 +49,9 @@ constexpr int GEMM_THREADS = 512;
 constexpr int LIN_THREADS = 640;        // linear kernel: + warps 16-19 = second epilogue set
 constexpr int SPLIT_THREADS = 256;      // warps 8-15
 constexpr int SMEM_MISC = 4096;         // barriers, tmem pointer, bias
-constexpr int GEMM_SMEM = OPERAND_BYTES + 1024 + SMEM_MISC;
+constexpr int STATS_MAX_N = 256;        // fused column statistics: per-CTA float64 accumulators [2][n] + quarter partials of both sets
+constexpr int SMEM_STATS = 2 * STATS_MAX_N * 8 + 2 * 4 * 64 * 4;
+constexpr int GEMM_SMEM = OPERAND_BYTES + 1024 + SMEM_MISC + SMEM_STATS;
 
 enum Epilogue { EPI_BIAS = 0, EPI_BIAS_TANH = 1, EPI_TANH_GRAD = 2, EPI_BIAS_SELECT = 3, EPI_BIAS_ADD = 4,
                 EPI_ROWMASK = 5,          // rows without neighbours (rowptr) give 0: backward of the row select, no mask pass
@@ -73,6 +75,8 @@ struct LinearParams {
   double* tk_s;                      // [m, tk_lists, tk_k]
   int64_t* tk_i;                     // [m, tk_lists, tk_k], pre-set to -1
   int store_out;                     // write the [m, n] matrix as well
+  // fused BatchNorm statistics (EPI_BIAS, n <= STATS_MAX_N): per-CTA column sums of y and y^2 over the rows < m
+  double* col_partial;               // [grid, 2, n] or null
 };
 constexpr int TK_MAX = 4;
 
@@ -102,6 +106,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
   float* bias_s = reinterpret_cast<float*>(misc + 512);     // up to 768 floats
+  double* stat_acc = reinterpret_cast<double*>(misc + SMEM_MISC);                       // [2][n]
+  float* stat_part = reinterpret_cast<float*>(misc + SMEM_MISC + 2 * STATS_MAX_N * 8);  // [2 sets][4 quarters][64]
   const uint32_t a_full = smem_u32(bars + 0), a_ready = smem_u32(bars + A_STAGES), a_empty = smem_u32(bars + 2 * A_STAGES);
   const uint32_t lo_empty = smem_u32(bars + 3 * A_STAGES), b_full = smem_u32(bars + 3 * A_STAGES + LO_STAGES);
   const uint32_t b_empty = smem_u32(bars + 3 * A_STAGES + LO_STAGES + B_STAGES);
@@ -129,6 +135,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   }
   if (!TOPK)
     for (int i = threadIdx.x; i < p.n; i += LIN_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  if (!TOPK && p.col_partial)
+    for (int i = threadIdx.x; i < 2 * p.n; i += LIN_THREADS) stat_acc[i] = 0.0;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -408,6 +416,31 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           sts128(out_addr + trow * 128 + ((j ^ (trow & 7)) << 4), make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]));
         fence_proxy_async();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+        if (!TOPK && p.col_partial) {
+          // column sums of this [128 x 32] chunk straight from the staging tile: thread (quarter, column) adds its 32 rows,
+          // the four quarters are combined in fixed order into the CTA's float64 accumulators (pc_col_stats fused away)
+          const int t128 = quad * 32 + lane, cc = t128 & 31, qtr = t128 >> 5;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int rw = qtr * 32 + rr;
+            if (int64_t(m0) + rw < p.m) {
+              const float v = lds32(out_addr + rw * 128 + ((((cc >> 2) ^ (rw & 7)) << 4) | ((cc & 3) << 2)));
+              s1 += v;
+              s2 = fmaf(v, v, s2);
+            }
+          }
+          float* part = stat_part + (set * 4 + qtr) * 64;
+          part[cc] = s1;
+          part[32 + cc] = s2;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+          if (t128 < 64) {
+            const int which = t128 >> 5;
+            const float* pp = stat_part + set * 4 * 64 + which * 32 + cc;
+            const float tot = ((pp[0] + pp[64]) + pp[128]) + pp[192];
+            stat_acc[which * p.n + n + cc] += double(tot);
+          }
+        }
         if (issuer) {
           const bool first = n < p.split;
           const CUtensorMap* map = first ? &map_out0 : &map_out1;
@@ -426,6 +459,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
     tk_flush();
+    if (!TOPK && p.col_partial) {
+      asm volatile("bar.sync 3, 256;" ::: "memory");       // both epilogue sets are done accumulating
+      const int t256 = set * 128 + quad * 32 + lane;
+      for (int i = t256; i < 2 * p.n; i += 256) p.col_partial[int64_t(blockIdx.x) * 2 * p.n + i] = stat_acc[i];
+    }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
@@ -689,19 +727,31 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int pa
   out[i] = acc;
 }
 
+__global__ void reduce_partials_f64_kernel(const double* __restrict__ partial, int parts, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int c = 0; c < parts; ++c) acc += partial[int64_t(c) * n + i];
+  out[i] = acc;
+}
+
 // ---------------------------------------------------------------- host side
 }  // namespace
 }  // namespace pc
 
 using namespace pc;
 
-extern "C" size_t pc_linear_workspace_bytes(int n, int k) { return align_up(size_t(n) * k * sizeof(float), 256) * 2; }
+extern "C" size_t pc_linear_workspace_bytes(int n, int k) {
+  return align_up(size_t(n) * k * sizeof(float), 256) * 2 + size_t(sm_count()) * 2 * size_t(n) * sizeof(double);
+}
 
 extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, const float* w, int n, const float* bias,
                                 int epilogue, const float* aux, int64_t ld_aux, const int64_t* rowptr, float* out0,
-                                int64_t ld0, int split, float* out1, int64_t ld1, void* workspace, size_t workspace_bytes,
-                                pc_stream_t stream) {
+                                int64_t ld0, int split, float* out1, int64_t ld1, double* col_sums, void* workspace,
+                                size_t workspace_bytes, pc_stream_t stream) {
   PC_REQUIRE(m >= 0, PC_ERR_INVALID, "linear: negative row count");
+  PC_REQUIRE(!col_sums || (m > 0 && epilogue == EPI_BIAS && n <= STATS_MAX_N), PC_ERR_UNSUPPORTED,
+             "linear: fused column statistics need epilogue 0, n <= %d and at least one row", STATS_MAX_N);
   if (m == 0) return PC_OK;
   PC_REQUIRE(a && w && out0 && workspace, PC_ERR_INVALID, "linear: null pointer");
   PC_REQUIRE(k >= BK && k % BK == 0 && k <= 4096, PC_ERR_UNSUPPORTED, "linear: k=%d must be a multiple of %d", k, BK);
@@ -760,8 +810,13 @@ extern "C" int pc_linear_tf32x3(const float* a, int64_t m, int k, int64_t lda, c
   const int64_t tiles = ((m + BM - 1) / BM) * p.n_tiles;
   const int grid = int(tiles < sm_count() ? tiles : sm_count());
   p.tk_k = 0; p.tk_lists = 0; p.tiles_per_cta = 0; p.tk_s = nullptr; p.tk_i = nullptr; p.store_out = 1;
+  p.col_partial = col_sums ? reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 2 * align_up(size_t(n) * k * sizeof(float), 256)) : nullptr;
   linear_tf32x3_kernel<false><<<grid, LIN_THREADS, GEMM_SMEM, st>>>(map_a, map_whi, map_wlo, map_out0, map_out1, map_aux, p);
   PC_LAUNCH_CHECK();
+  if (col_sums) {   // CTA partials summed in CTA order: bit-reproducible
+    reduce_partials_f64_kernel<<<(2 * n + 255) / 256, 256, 0, st>>>(p.col_partial, grid, 2 * n, col_sums);
+    PC_LAUNCH_CHECK();
+  }
   return PC_OK;
 }
 
@@ -810,6 +865,7 @@ extern "C" int pc_type_scores_topk(const float* a, int64_t m, int k, int64_t lda
   p.bias = nullptr; p.out0 = out; p.ld0 = int(ld_out); p.split = n; p.out1 = nullptr; p.ld1 = 0;
   p.epilogue = EPI_BIAS; p.aux = nullptr; p.ld_aux = 0; p.rowptr = nullptr;
   p.tk_k = topk; p.tk_lists = 2 * sc.max_segs; p.tiles_per_cta = sc.per; p.store_out = out ? 1 : 0;
+  p.col_partial = nullptr;
   cudaStream_t st = as_stream(stream);
   char* ws = reinterpret_cast<char*>(workspace);
   const size_t wbytes = align_up(size_t(n) * k * sizeof(float), 256);

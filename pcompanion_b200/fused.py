@@ -49,9 +49,9 @@ def ffn_forward_core(x, w0, b0, gamma, beta, w3, b3, w5, b5, training, eps, mome
     Returns (z1, a1, a2, h, mean, rstd, count); running statistics are updated in place with nn.BatchNorm1d's rule
     (momentum None = cumulative average over num_batches_tracked, unbiased variance)."""
     n = x.shape[0]
-    z1 = ops.linear_tc(x, w0, b0)
     if training or run_mean is None:
-        sums, count = _allreduce_sums(ops.col_stats(z1), n, group, sync_bn, total)
+        z1, local_sums = ops.linear_tc(x, w0, b0, col_stats=True)     # batch statistics in the GEMM's epilogue
+        sums, count = _allreduce_sums(local_sums, n, group, sync_bn, total)
         if training and count <= 1:
             raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(z1.shape)}")
         mean64 = sums[0] / count
@@ -62,6 +62,7 @@ def ffn_forward_core(x, w0, b0, gamma, beta, w3, b3, w5, b5, training, eps, mome
                 run_mean.mul_(1 - m_).add_(mean64.to(F32), alpha=m_)
                 run_var.mul_(1 - m_).add_((var64 * (count / max(count - 1, 1))).to(F32), alpha=m_)
     else:
+        z1 = ops.linear_tc(x, w0, b0)
         count = n
         mean64, var64 = run_mean.double(), run_var.double()
     rstd64 = torch.rsqrt(var64 + eps)

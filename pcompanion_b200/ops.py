@@ -372,9 +372,11 @@ EPI_BIAS, EPI_BIAS_TANH, EPI_TANH_GRAD, EPI_BIAS_SELECT, EPI_BIAS_ADD, EPI_ROWMA
 
 def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
               aux: Optional[torch.Tensor] = None, rowptr: Optional[torch.Tensor] = None, split: Optional[int] = None,
-              out0: Optional[torch.Tensor] = None, out1: Optional[torch.Tensor] = None):
+              out0: Optional[torch.Tensor] = None, out1: Optional[torch.Tensor] = None, col_stats: bool = False):
     """epilogue(A . W^T + bias) on the tensor cores (pc_linear_tf32x3).  Returns one [m, n] tensor, or
-    ([m, split], [m, n - split]) when `split` is given.  out0 / out1 may be preallocated (strided) views."""
+    ([m, split], [m, n - split]) when `split` is given.  out0 / out1 may be preallocated (strided) views.
+    col_stats=True (plain bias epilogue, n <= 256) also returns float64 [2, n]: column sums of the output and of its
+    square, taken in the GEMM's epilogue."""
     m, k = a.shape
     n = w.shape[0]
     if a.stride(1) != 1 or w.stride() != (k, 1):
@@ -385,11 +387,14 @@ def linear_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
     if out1 is None and split_ < n:
         out1 = torch.empty(m, n - split_, dtype=F32, device=a.device)
     ws = _lib.workspace(_lib.LIB.pc_linear_workspace_bytes(n, k), a.device)
+    sums = torch.empty(2, n, dtype=F64, device=a.device) if col_stats else None
     call("pc_linear_tf32x3", _f32_cuda(a, "a"), m, k, a.stride(0), dev(w, F32, "w"), n, dev(bias, F32, "bias"), epilogue,
          _f32_cuda(aux, "aux") if aux is not None else None, aux.stride(0) if aux is not None else 0,
          dev(rowptr, I64, "rowptr"), _f32_cuda(out0, "out0"), out0.stride(0), split_,
          _f32_cuda(out1, "out1") if out1 is not None else None, out1.stride(0) if out1 is not None else 0,
-         dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+         dev(sums, F64, "col_sums"), dev(ws, torch.uint8, "ws"), ws.numel(), stream())
+    if col_stats:
+        return out0, sums
     return out0 if out1 is None else (out0, out1)
 
 

@@ -110,6 +110,25 @@ def test_wgrad_strided_operands():
     close(db, dy.double().sum(0).cpu().numpy(), what="db strided")
 
 
+@pytest.mark.parametrize("m", [1, 127, 128, 4097, 300_001])
+def test_linear_fused_column_statistics(m):
+    """BatchNorm statistics taken in the GEMM epilogue (pc_linear_tf32x3 col_sums): sums of the output it wrote and of its
+    square over exactly the m rows (ragged last tile excluded), deterministic."""
+    from pcompanion_b200 import ops
+    g = torch.Generator(device=dev()).manual_seed(m)
+    a = torch.randn(m, 128, generator=g, device=dev())
+    w = torch.randn(256, 128, generator=g, device=dev()) * 0.1
+    b = torch.randn(256, generator=g, device=dev())
+    y, sums = ops.linear_tc(a, w, b, col_stats=True)
+    assert torch.equal(y, ops.linear_tc(a, w, b))                      # the output itself is unchanged
+    np.testing.assert_allclose(sums[0].cpu().numpy(), y.double().sum(0).cpu().numpy(), rtol=2e-6, atol=1e-6 * m ** 0.5)
+    np.testing.assert_allclose(sums[1].cpu().numpy(), (y.double() ** 2).sum(0).cpu().numpy(), rtol=2e-6)
+    assert torch.equal(ops.linear_tc(a, w, b, col_stats=True)[1], sums)
+    w1 = torch.randn(128, 128, generator=g, device=dev()) * 0.1         # one n-tile
+    y1, s1 = ops.linear_tc(a, w1, None, col_stats=True)
+    np.testing.assert_allclose(s1[1].cpu().numpy(), (y1.double() ** 2).sum(0).cpu().numpy(), rtol=2e-6)
+
+
 def test_linear_autograd_function_matches_torch_autograd():
     """nn.Linear drop-in on the tcgen05 kernels (forward, dgrad, wgrad): the shapes of the Product2Vec projections and of
     P-Companion's type projection (64 -> 128) / item projection (128 -> 128)."""
