@@ -162,10 +162,11 @@ int pc_wgrad_tf32x3(const float* dy, int64_t m, int n, int64_t ld_dy, const floa
 size_t pc_col_reduce_workspace_bytes(int n);
 int pc_col_stats(const float* x, int64_t m, int n, int64_t ldx, double* sums, void* workspace, size_t workspace_bytes,
                  pc_stream_t stream);
-/* sums[0, c] = sum of x[r, c] over the rows r with neighbours (rowptr[r+1] > rowptr[r]), sums[1, :] = 0: the out-projection's
- * bias gradient under the "rows without neighbours keep ffn(x)" select of product2vec.py:76, without materialising the
- * masked gradient.  Same fixed-order float64 reduction and workspace as pc_col_stats. */
-int pc_col_sum_selected(const float* x, int64_t m, int n, int64_t ldx, const int64_t* rowptr, double* sums, void* workspace,
+/* sums[0, c] = sum of x[r, c] over the rows r WITHOUT neighbours (rowptr[r+1] == rowptr[r]), sums[1, :] = 0.  Under the
+ * "rows without neighbours keep ffn(x)" select of product2vec.py:76 the out-projection's bias gradient is the column
+ * sum of d_emb over all rows (a by-product of pc_wgrad_tf32x3) minus this; rows with neighbours are skipped before their
+ * data is read.  Same fixed-order float64 reduction and workspace as pc_col_stats. */
+int pc_col_sum_unselected(const float* x, int64_t m, int n, int64_t ldx, const int64_t* rowptr, double* sums, void* workspace,
                         size_t workspace_bytes, pc_stream_t stream);
 int pc_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* x, int64_t ldx, int64_t m, int n, const float* mean,
                      const float* rstd, double* sums, void* workspace, size_t workspace_bytes, pc_stream_t stream);

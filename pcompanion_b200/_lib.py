@@ -37,7 +37,7 @@ PROTOTYPES = {
     "pc_gat_delta": (c_int, [P, P, c_int64, c_int64, c_int, P, P]),
     "pc_col_reduce_workspace_bytes": (c_size_t, [c_int]),
     "pc_col_stats": (c_int, [P, c_int64, c_int, c_int64, P, P, c_size_t, P]),
-    "pc_col_sum_selected": (c_int, [P, c_int64, c_int, c_int64, P, P, P, c_size_t, P]),
+    "pc_col_sum_unselected": (c_int, [P, c_int64, c_int, c_int64, P, P, P, c_size_t, P]),
     "pc_bn_bwd_reduce": (c_int, [P, c_int64, P, c_int64, c_int64, c_int, P, P, P, P, c_size_t, P]),
     "pc_scale_shift_tanh": (c_int, [P, c_int64, c_int64, c_int, P, P, c_int, P, c_int64, P]),
     "pc_affine2": (c_int, [P, c_int64, P, c_int64, c_int64, c_int, P, P, P, P, c_int64, P]),

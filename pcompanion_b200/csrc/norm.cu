@@ -16,7 +16,9 @@ constexpr int RED_THREADS = 256;
 
 // sums[0, c] = sum_r f0(r, c), sums[1, c] = sum_r f1(r, c) over rows, n4 = n / 4 column groups.
 // MODE 0: f0 = x, f1 = x^2.   MODE 1: f0 = dy, f1 = dy * (x - mean) * rstd.
-// MODE 2: f0 = x on rows with neighbours (rowptr[r+1] > rowptr[r]), 0 elsewhere; f1 = 0  (bias gradient of the row select).
+// MODE 2: f0 = x on the rows WITHOUT neighbours (rowptr[r+1] == rowptr[r]), 0 elsewhere; f1 = 0: the correction of the
+// out-projection's bias gradient under the row select.  Rows with neighbours are skipped before their data is touched, so
+// on a graph with few isolated nodes the pass reads little more than rowptr.
 template <int MODE>
 __global__ void __launch_bounds__(RED_THREADS)
 col_reduce_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb, int64_t m, int n4,
@@ -36,7 +38,7 @@ col_reduce_kernel(const float* __restrict__ a, int64_t lda, const float* __restr
     const int64_t r_beg = int64_t(blockIdx.x) * rows_per_cta;
     const int64_t r_end = min(m, r_beg + rows_per_cta);
     for (int64_t r = r_beg + rl; r < r_end; r += row_lanes) {
-      if (MODE == 2 && rowptr[r + 1] <= rowptr[r]) continue;
+      if (MODE == 2 && rowptr[r + 1] > rowptr[r]) continue;
       const float4 x = ld_stream4(reinterpret_cast<const float4*>(a + r * lda) + cg);
       if (MODE == 2) {
         s0[0] += x.x; s0[1] += x.y; s0[2] += x.z; s0[3] += x.w;
@@ -168,9 +170,9 @@ extern "C" int pc_col_stats(const float* x, int64_t m, int n, int64_t ldx, doubl
   return col_reduce<0>(x, ldx, nullptr, 4, m, n, nullptr, nullptr, nullptr, sums, workspace, workspace_bytes, as_stream(stream));
 }
 
-extern "C" int pc_col_sum_selected(const float* x, int64_t m, int n, int64_t ldx, const int64_t* rowptr, double* sums, void* workspace,
+extern "C" int pc_col_sum_unselected(const float* x, int64_t m, int n, int64_t ldx, const int64_t* rowptr, double* sums, void* workspace,
                                    size_t workspace_bytes, pc_stream_t stream) {
-  PC_REQUIRE(rowptr, PC_ERR_INVALID, "col_sum_selected: null rowptr");
+  PC_REQUIRE(rowptr, PC_ERR_INVALID, "col_sum_unselected: null rowptr");
   return col_reduce<2>(x, ldx, nullptr, 4, m, n, nullptr, nullptr, rowptr, sums, workspace, workspace_bytes, as_stream(stream));
 }
 

@@ -213,12 +213,13 @@ class _P2VGraphLayer(torch.autograd.Function):
         n = x.shape[0]
         # rows without neighbours kept ffn(x) in the forward (product2vec.py:76): their gradient bypasses the attention.
         # No masked copies of d_emb: the dO GEMM zeroes those rows in its epilogue, dW_o needs no mask (their O rows are
-        # zero), the bias gradient is a selected column sum, and the d_h GEMM adds d_emb back on exactly those rows.
+        # zero), the bias gradient is the wgrad kernel's column sum minus the sum over those rows, and the d_h GEMM adds d_emb back
+        # on exactly those rows.
         d_emb = d_emb.contiguous()
         # out-projection
         ops.linear_tc(d_emb, w_o.t().contiguous(), None, ops.EPI_ROWMASK, rowptr=graph.rowptr, out0=qg[:, 128:])   # dO next to Q
-        dw_o, _ = ops.wgrad_tc(d_emb, o, want_bias=False)
-        db_o = ops.col_sum_selected(d_emb, graph.rowptr).to(F32)
+        dw_o, db_all = ops.wgrad_tc(d_emb, o)
+        db_o = db_all - ops.col_sum_unselected(d_emb, graph.rowptr).to(F32)
         # attention
         if plan is None:
             dqkv = torch.empty(n, 384, dtype=F32, device=x.device)

@@ -429,12 +429,12 @@ def col_stats(x: torch.Tensor) -> torch.Tensor:
     return sums
 
 
-def col_sum_selected(x: torch.Tensor, rowptr: torch.Tensor) -> torch.Tensor:
-    """float64 [n]: column sums of x over the rows that have neighbours (rowptr[r+1] > rowptr[r])."""
+def col_sum_unselected(x: torch.Tensor, rowptr: torch.Tensor) -> torch.Tensor:
+    """float64 [n]: column sums of x over the rows that have NO neighbours (rowptr[r+1] == rowptr[r])."""
     m, n = x.shape
     sums = torch.empty(2, n, dtype=F64, device=x.device)
     ws = _col_reduce_ws(n, x.device)
-    call("pc_col_sum_selected", _f32_cuda(x, "x"), m, n, x.stride(0), dev(rowptr, I64, "rowptr"), dev(sums, F64, "sums"),
+    call("pc_col_sum_unselected", _f32_cuda(x, "x"), m, n, x.stride(0), dev(rowptr, I64, "rowptr"), dev(sums, F64, "sums"),
          dev(ws, torch.uint8, "ws"), ws.numel(), stream())
     return sums[0]
 

@@ -55,14 +55,14 @@ def test_linear_epilogues_and_split_outputs():
     ref_o = (a.double() @ w3.double().T + b3.double()).cpu().numpy()
     keep = (np.arange(m) % 3 != 0)[:, None]
     close(out, np.where(keep, ref_o, h.cpu().numpy()), what="select")
-    # backward of the select without masked copies: zero rows (5), add aux on the unselected rows only (6), selected column sum
+    # backward of the select without masked copies: zero rows (5), add aux on the unselected rows only (6), their column sum
     masked = ops.linear_tc(a, w3, b3, ops.EPI_ROWMASK, rowptr=rowptr)
     close(masked, np.where(keep, ref_o, 0.0), what="rowmask")
     assert bool((masked[~torch.tensor(keep[:, 0], device=dev())] == 0).all())
     added = ops.linear_tc(a, w3, b3, ops.EPI_ADD_UNSELECTED, aux=h, rowptr=rowptr)
     close(added, ref_o + np.where(keep, 0.0, h.cpu().numpy()), what="add unselected")
-    sel = ops.col_sum_selected(h, rowptr)
-    np.testing.assert_allclose(sel.cpu().numpy(), (h.double().cpu().numpy() * keep).sum(0), rtol=1e-12, atol=1e-12)
+    sel = ops.col_sum_unselected(h, rowptr)
+    np.testing.assert_allclose(sel.cpu().numpy(), (h.double().cpu().numpy() * ~keep).sum(0), rtol=1e-12, atol=1e-12)
     # strided A (a column slice of a wider tensor)
     wide = torch.randn(m, 384, generator=g, device=dev())
     ys = ops.linear_tc(wide[:, 128:256], w3, b3)
