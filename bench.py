@@ -608,7 +608,9 @@ def pcompanion_leg(args, rank, world, dev, batch, cpu=False):
         # launch-bound regime: the whole step (forward + loss + backward + Adam) captured once in a CUDA graph and replayed
         eager = {"ms_per_step": ms, "samples_per_s": b / (ms * 1e-3), "e2e_ms_per_step": e2e_ms, "c_abi_calls_per_step": launches // args.steps}
         gopt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=cfg.LEARNING_RATE, capturable=True)
-        gstep = pc.GraphedTrainStep(model, gopt, bt_dev)
+        l1 = _lib.LAUNCHES
+        gstep = pc.GraphedTrainStep(model, gopt, bt_dev)                 # 3 warm-up steps + 1 captured step
+        launches = (_lib.LAUNCHES - l1) // 4 * args.steps                # C-ABI calls inside one replay x timed replays
         for _ in range(args.warmup):
             gstep(bt_dev)
         ms, _ = timed_steps(lambda: gstep(bt_dev), args.steps, dev, world, flush)
