@@ -718,13 +718,17 @@ def retrieval_leg(args, rank, world, dev, dense=False, cpu=False):
     warm_up(step, args.warmup, 1.5, dev, world)
     sampler.mark()
     launches0 = _lib.LAUNCHES
-    _lib.PROFILE = []
     ms, _ = timed_steps(step, args.steps, dev, world)
-    prof, _lib.PROFILE = _lib.PROFILE, None
     launches = _lib.LAUNCHES - launches0
     clocks = sampler.stop()
     step_e2e()
     e2e_ms, _ = timed_steps(step_e2e, args.steps, dev, world)
+    # per-kernel device time from a separate profiled pass (CUDA events around every C-ABI call)
+    _lib.PROFILE = []
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    prof, _lib.PROFILE = _lib.PROFILE, None
     per_call = {}
     for name, s0, s1 in prof:
         per_call[name] = per_call.get(name, 0.0) + s0.elapsed_time(s1) / args.steps
