@@ -78,6 +78,8 @@ class ClockSampler:
     def __init__(self, index: int):
         self.proc = None
         self.t_mark = None
+        if int(os.environ.get("RANK", 0)) != 0:
+            return          # one sampler per job (rank 0's GPU): eight nvidia-smi pollers perturb millisecond-scale steps
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
