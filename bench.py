@@ -39,6 +39,7 @@ EDGES_PER_GPU = 20_000_000
 TRIPLETS = 131_072
 KNEG = 5
 SEED = 1234
+SHORT_LEG_SECONDS = 0.4      # sub-records whose step is a few ms are timed over at least this long (a multiple of --steps)
 FP64_TFLOPS_NOMINAL = 37.0   # B200 vector fp64 (HGX B200: 296 TFLOP/s per 8 GPUs); no measured figure in MEASURED_PEAKS.json
 
 # algorithmic bytes of the three sparse kernels (fp32, per edge / per node)
@@ -160,9 +161,7 @@ def warm_up(fn, min_steps, min_seconds, dev, world):
         torch.cuda.synchronize()
 
 
-def timed_steps(fn, steps, dev, world, flush=None):
-    """Average device time of `steps` calls of fn (CUDA events on the current stream, barrier + synchronize on both sides,
-    max over ranks).  With `flush` every step is timed on its own and the L2 flush between the steps is not."""
+def _time_once(fn, steps, dev, world, flush):
     torch.cuda.synchronize()
     if world > 1:
         _dist().barrier()
@@ -187,6 +186,19 @@ def timed_steps(fn, steps, dev, world, flush=None):
     if world > 1:
         _dist().barrier()
     return max_over_ranks([ms], dev, world)[0], out
+
+
+def timed_steps(fn, steps, dev, world, flush=None, min_seconds=0.0):
+    """Average device time of `steps` calls of fn (CUDA events on the current stream, barrier + synchronize on both sides,
+    max over ranks).  With `flush` every step is timed on its own and the L2 flush between the steps is not.
+    min_seconds (legs whose step is a few milliseconds): when the K steps took less than that, the measurement is repeated
+    with a multiple of K steps that fills it - a single stall of the clock sampler's nvidia-smi poll (tens of ms) would
+    otherwise double a 30 ms region.  The step count is derived from the max-over-ranks time: the same on every rank."""
+    ms, out = _time_once(fn, steps, dev, world, flush)
+    if min_seconds > 0.0 and ms * steps < min_seconds * 1e3:
+        reps = min(int(math.ceil(min_seconds * 1e3 / max(ms * steps, 1e-3))), 200)
+        ms, out = _time_once(fn, steps * reps, dev, world, flush)
+    return ms, out
 
 
 # ============================================================================= GAT leg, one GPU (C2)
@@ -600,11 +612,11 @@ def pcompanion_leg(args, rank, world, dev, batch, cpu=False):
     warm_up(lambda: step(bt_dev), args.warmup, 1.0, dev, world)
     sampler.mark()
     l0 = _lib.LAUNCHES
-    ms, _ = timed_steps(lambda: step(bt_dev), args.steps, dev, world, flush)
+    ms, _ = timed_steps(lambda: step(bt_dev), args.steps, dev, world, flush, SHORT_LEG_SECONDS)
     launches = _lib.LAUNCHES - l0
     clocks = sampler.stop()
     step_e2e()
-    e2e_ms, _ = timed_steps(step_e2e, args.steps, dev, world, flush)
+    e2e_ms, _ = timed_steps(step_e2e, args.steps, dev, world, flush, SHORT_LEG_SECONDS)
     eager = None
     if small and world == 1:
         # launch-bound regime: the whole step (forward + loss + backward + Adam) captured once in a CUDA graph and replayed
@@ -615,12 +627,12 @@ def pcompanion_leg(args, rank, world, dev, batch, cpu=False):
         launches = (_lib.LAUNCHES - l1) // 4 * args.steps                # C-ABI calls inside one replay x timed replays
         for _ in range(args.warmup):
             gstep(bt_dev)
-        ms, _ = timed_steps(lambda: gstep(bt_dev), args.steps, dev, world, flush)
+        ms, _ = timed_steps(lambda: gstep(bt_dev), args.steps, dev, world, flush, SHORT_LEG_SECONDS)
 
         def gstep_e2e():
             loss_host.copy_(gstep(host).detach(), non_blocking=True)
         gstep_e2e()
-        e2e_ms, _ = timed_steps(gstep_e2e, args.steps, dev, world, flush)
+        e2e_ms, _ = timed_steps(gstep_e2e, args.steps, dev, world, flush, SHORT_LEG_SECONDS)
     if rank != 0:
         return None
     peak, peak_src = measured_peaks()
@@ -642,7 +654,7 @@ def pcompanion_leg(args, rank, world, dev, batch, cpu=False):
                          "note": "whole step against the [B,T] similarity write, the type-table read / gradient / Adam traffic "
                                  "and the per-sample rows; small batches are launch-latency bound, not bandwidth bound"},
             "cpu_baseline": cpu_baseline_pcompanion(cfg, b) if cpu else None, "clocks": clocks,
-            "cuda_graph": eager is not None, "eager": eager,
+            "cuda_graph": eager is not None, "eager": eager, "min_timed_seconds": SHORT_LEG_SECONDS,
             "e2e": {"value": b * world / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * world,
                     "d2h_bytes_per_step": 4 * world},
@@ -720,11 +732,11 @@ def retrieval_leg(args, rank, world, dev, dense=False, cpu=False):
     warm_up(step, args.warmup, 1.5, dev, world)
     sampler.mark()
     launches0 = _lib.LAUNCHES
-    ms, _ = timed_steps(step, args.steps, dev, world)
+    ms, _ = timed_steps(step, args.steps, dev, world, None, SHORT_LEG_SECONDS)
     launches = _lib.LAUNCHES - launches0
     clocks = sampler.stop()
     step_e2e()
-    e2e_ms, _ = timed_steps(step_e2e, args.steps, dev, world)
+    e2e_ms, _ = timed_steps(step_e2e, args.steps, dev, world, None, SHORT_LEG_SECONDS)
     # per-kernel device time from a separate profiled pass (CUDA events around every C-ABI call)
     _lib.PROFILE = []
     for _ in range(args.steps):
@@ -774,6 +786,7 @@ def retrieval_leg(args, rank, world, dev, dense=False, cpu=False):
                                    "fused candidate top-K + exact fp64 re-scoring" if dense else "type-segmented exact fp64 scoring "
                                    "(device-side grouping), per-shard lists all-gathered and merged"),
                        "l2": "the catalog (5.12 GB per 10M rows) exceeds the 126 MB L2; no flush needed"},
+            "min_timed_seconds": SHORT_LEG_SECONDS,
             "roofline": roofline, "abi_ms_per_step": {n_: round(v, 4) for n_, v in sorted(per_call.items(), key=lambda kv: -kv[1])},
             "cpu_baseline": cpu_baseline_retrieval() if cpu else None,
             "clocks": clocks,
