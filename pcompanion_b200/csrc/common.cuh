@@ -94,6 +94,28 @@ __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t dst, uint32
   x ^= x >> 15;
   return x;
 }
+// Keep bits of one edge for all H heads (bit h = kept): the (seed, dst, src) rounds are shared, only the last round depends
+// on the head.  The GAT kernels call this ONCE per edge in one lane (the lane that loaded the edge's id) and hand the bits
+// to the arithmetic by shuffle, instead of evaluating the hash in every lane of every head for every edge.
+template <int H>
+__device__ __forceinline__ uint32_t keep_bits(uint64_t seed, uint32_t dst, uint32_t src, uint32_t drop_threshold) {
+  uint32_t x = dst * 0x9E3779B1u + uint32_t(seed);
+  x ^= x >> 15;
+  x *= 0x2C1B3C6Du;
+  x ^= src * 0x85EBCA77u + uint32_t(seed >> 32);
+  x ^= x >> 13;
+  x *= 0x297A2D39u;
+  uint32_t bits = 0;
+#pragma unroll
+  for (uint32_t h = 0; h < uint32_t(H); ++h) {
+    uint32_t y = x + h * 0xC2B2AE3Du;
+    y ^= y >> 16;
+    y *= 0x7FEB352Du;
+    y ^= y >> 15;
+    bits |= uint32_t(y >= drop_threshold) << h;
+  }
+  return bits;
+}
 // returns 0 (dropped) or 1/(1-p)
 __device__ __forceinline__ float keep_scale(uint64_t seed, uint32_t dst, uint32_t src, uint32_t head,
                                             uint32_t drop_threshold, float inv_keep) {

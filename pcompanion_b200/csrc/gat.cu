@@ -127,8 +127,8 @@ gat_fwd_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, cons
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      int my_col = 0;
-      if (DROP) my_col = lane < cnt ? col[base + lane] : 0;
+      uint32_t my_keep = 0;       // lane l: keep bits (one per head) of edge base + l
+      if (DROP && lane < cnt) my_keep = keep_bits<H>(drop.seed, i_id, uint32_t(col[base + lane]), drop.threshold);
       for (int t = 0; t < cnt; t += U) {
         float4 k[U], v[U];
 #pragma unroll
@@ -159,10 +159,7 @@ gat_fwd_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, cons
             const float p = exp2f(s[u] - m_new);
             l += p;
             float pv = p;
-            if (DROP) {
-              const int src = __shfl_sync(FULL, my_col, (t + u) & 31);
-              pv *= keep_scale(drop.seed, i_id, uint32_t(src), head, drop.threshold, drop.inv_keep);
-            }
+            if (DROP) pv *= ((__shfl_sync(FULL, my_keep, (t + u) & 31) >> head) & 1u) ? drop.inv_keep : 0.f;
             fma4(acc, pv, v[u]);
           }
         }
@@ -216,8 +213,8 @@ gat_bwd_dst_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
     float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      int my_col = 0;
-      if (DROP) my_col = lane < cnt ? col[base + lane] : 0;
+      uint32_t my_keep = 0;
+      if (DROP && lane < cnt) my_keep = keep_bits<H>(drop.seed, i_id, uint32_t(col[base + lane]), drop.threshold);
       for (int t = 0; t < cnt; t += U) {
         float4 k[U], v[U];
 #pragma unroll
@@ -236,10 +233,7 @@ gat_bwd_dst_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
             const float s2 = group_sum<G>(dot4(q, k[u]));
             const float p = exp2f(s2 - lse2);
             float da = group_sum<G>(dot4(go, v[u]));
-            if (DROP) {
-              const int src = __shfl_sync(FULL, my_col, (t + u) & 31);
-              da *= keep_scale(drop.seed, i_id, uint32_t(src), head, drop.threshold, drop.inv_keep);
-            }
+            if (DROP) da *= ((__shfl_sync(FULL, my_keep, (t + u) & 31) >> head) & 1u) ? drop.inv_keep : 0.f;
             fma4(dq, p * (da - delta), k[u]);
           }
         }
@@ -309,8 +303,8 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
       const float4 v = ldg4(KV + j * KV4 + ROW4 + lane);
       for (int base = beg; base < end; base += 32) {
         const int cnt = min(32, end - base);
-        int my_row = 0;
-        if (DROP) my_row = lane < cnt ? row[base + lane] : 0;
+        uint32_t my_keep = 0;
+        if (DROP && lane < cnt) my_keep = keep_bits<H>(drop.seed, uint32_t(row[base + lane]), j_id, drop.threshold);
         for (int t = 0; t < cnt; t += U) {
           float4 qi[U], gi[U];
           float lse2[U], delta[U];
@@ -336,8 +330,7 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
               float da = group_sum<G>(dot4(gi[u], v));
               float pk = p;
               if (DROP) {
-                const int dst = __shfl_sync(FULL, my_row, (t + u) & 31);
-                const float ks = keep_scale(drop.seed, uint32_t(dst), j_id, head, drop.threshold, drop.inv_keep);
+                const float ks = ((__shfl_sync(FULL, my_keep, (t + u) & 31) >> head) & 1u) ? drop.inv_keep : 0.f;
                 da *= ks;
                 pk *= ks;
               }
