@@ -141,7 +141,7 @@ class CatalogIndex:
 class ShardedCatalog:
     """Catalog rows sharded contiguously over a process group: rank g owns rows
     [bounds[g], bounds[g+1]); queries are replicated; per-shard top-k lists are all-gathered and
-    merged.  Works with NCCL (CUDA tensors); the only collective is the [R, k] all-gather."""
+    merged.  Works with NCCL (CUDA tensors) and gloo; the only collective is one [R, 2k] all-gather."""
 
     def __init__(self, local_catalog: torch.Tensor, local_type_id: Optional[torch.Tensor], index_base: int,
                  num_types: Optional[int] = None, group=None):
@@ -154,10 +154,10 @@ class ShardedCatalog:
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
             return s, i
-        all_s = torch.empty(world, *s.shape, dtype=s.dtype, device=s.device)
-        all_i = torch.empty(world, *i.shape, dtype=i.dtype, device=i.device)
-        dist.all_gather_into_tensor(all_s, s, group=self.group)
-        dist.all_gather_into_tensor(all_i, i, group=self.group)
-        cat_s = all_s.permute(1, 0, 2).reshape(s.shape[0], world * k)
-        cat_i = all_i.permute(1, 0, 2).reshape(s.shape[0], world * k)
+        # ONE collective: the int64 indices travel as their float64 bit patterns next to the scores ([R, 2k] per rank)
+        packed = torch.cat([s, i.view(torch.float64)], dim=1).contiguous()
+        gathered = torch.empty(world, *packed.shape, dtype=torch.float64, device=s.device)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        cat_s = gathered[:, :, :k].permute(1, 0, 2).reshape(s.shape[0], world * k)
+        cat_i = gathered[:, :, k:].permute(1, 0, 2).reshape(s.shape[0], world * k).contiguous().view(torch.int64)
         return ops.topk_merge(cat_s, cat_i, k)
