@@ -219,7 +219,7 @@ def gat_single(args, dev):
     n, e = graph.n_rows, graph.num_edges
     cfg = make_cfg(dev)
     model = pc.Product2Vec(cfg).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE, fused=True)   # same Adam, one kernel for the 13 tensors
     g = torch.Generator(device=dev).manual_seed(SEED + 2)
     trip = torch.randint(0, n, (TRIPLETS, 2 + KNEG), generator=g, device=dev)
     x_dev = bpg.features
@@ -373,7 +373,7 @@ def gat_skewed_leg(args, dev):
         graph = ops.CSRGraph(base.rowptr, base.col, n, n, base._t, split_hubs=split)
         torch.manual_seed(SEED)
         model = pc.Product2Vec(cfg).to(dev).train()
-        opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+        opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE, fused=True)   # same Adam, one kernel for the 13 tensors
 
         def step():
             emb = model.forward_graph(x, graph)
@@ -456,7 +456,7 @@ def gat_partitioned(args, rank, world, dev, nodes_per_gpu=NODES_PER_GPU, edges_p
     cfg = make_cfg(dev)
     torch.manual_seed(SEED)                      # identical replicated weights on every rank
     model = pc.Product2Vec(cfg).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE, fused=True)   # same Adam, one kernel for the 13 tensors
     # triplets: anchors are local, positives / negatives are any product of the global graph; their rows come from
     # the owners through a row-fetch plan (built once: the index batch is fixed, as in the 1-GPU leg)
     trip_global = torch.cat([torch.randint(0, n_loc, (TRIPLETS, 1), generator=g, device=dev) + bounds[rank],
@@ -831,7 +831,7 @@ def c1_leg(args, dev, cpu=False):
     loader = DataLoader(ds, batch_size=256, shuffle=True, collate_fn=pc.collate_fn, num_workers=0)
     torch.manual_seed(SEED)
     model = pc.Product2Vec(cfg).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE, fused=True)   # same Adam, one kernel for the 13 tensors
 
     def epoch():
         model.train()

@@ -16,9 +16,6 @@ constexpr int RED_THREADS = 256;
 
 // sums[0, c] = sum_r f0(r, c), sums[1, c] = sum_r f1(r, c) over rows, n4 = n / 4 column groups.
 // MODE 0: f0 = x, f1 = x^2.   MODE 1: f0 = dy, f1 = dy * (x - mean) * rstd.
-// MODE 2: f0 = x on the rows WITHOUT neighbours (rowptr[r+1] == rowptr[r]), 0 elsewhere; f1 = 0: the correction of the
-// out-projection's bias gradient under the row select.  Rows with neighbours are skipped before their data is touched, so
-// on a graph with few isolated nodes the pass reads little more than rowptr.
 template <int MODE>
 __global__ void __launch_bounds__(RED_THREADS)
 col_reduce_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb, int64_t m, int n4,
@@ -38,11 +35,8 @@ col_reduce_kernel(const float* __restrict__ a, int64_t lda, const float* __restr
     const int64_t r_beg = int64_t(blockIdx.x) * rows_per_cta;
     const int64_t r_end = min(m, r_beg + rows_per_cta);
     for (int64_t r = r_beg + rl; r < r_end; r += row_lanes) {
-      if (MODE == 2 && rowptr[r + 1] > rowptr[r]) continue;
       const float4 x = ld_stream4(reinterpret_cast<const float4*>(a + r * lda) + cg);
-      if (MODE == 2) {
-        s0[0] += x.x; s0[1] += x.y; s0[2] += x.z; s0[3] += x.w;
-      } else if (MODE == 0) {
+      if (MODE == 0) {
         s0[0] += x.x; s0[1] += x.y; s0[2] += x.z; s0[3] += x.w;
         s1[0] += double(x.x) * x.x; s1[1] += double(x.y) * x.y; s1[2] += double(x.z) * x.z; s1[3] += double(x.w) * x.w;
       } else {
@@ -129,6 +123,38 @@ mask_split_kernel(const float* __restrict__ g, int64_t m, int n4, const int64_t*
   }
 }
 
+// Column sums over the rows WITHOUT neighbours.  Lane l of a warp tests row base + l (two coalesced rowptr loads per warp);
+// only the empty rows are then read, all lanes together, in ascending row order; per-CTA float64 partials in shared memory,
+// summed in CTA order by col_reduce_final_kernel.  On a graph with few isolated nodes this reads little more than rowptr.
+__global__ void __launch_bounds__(RED_THREADS)
+col_sum_unselected_kernel(const float* __restrict__ x, int64_t ldx, int64_t m, int n, const int64_t* __restrict__ rowptr,
+                          double* __restrict__ partial) {
+  extern __shared__ double sm[];   // [warps][n]
+  const int lane = lane_id(), w = warp_id(), warps = RED_THREADS / 32;
+  double* mine = sm + w * n;
+  for (int c = lane; c < n; c += 32) mine[c] = 0.0;
+  __syncwarp();
+  const int64_t rows_per_cta = (ceil_div(m, int64_t(gridDim.x)) + 31) / 32 * 32;
+  const int64_t r_beg = int64_t(blockIdx.x) * rows_per_cta, r_end = min(m, r_beg + rows_per_cta);
+  for (int64_t base = r_beg + int64_t(w) * 32; base < r_end; base += int64_t(warps) * 32) {
+    const int64_t r = base + lane;
+    uint32_t empty = __ballot_sync(FULL, r < r_end && rowptr[r + 1] == rowptr[r]);
+    while (empty) {
+      const int l = __ffs(empty) - 1;
+      empty &= empty - 1;
+      const float* row = x + (base + l) * ldx;
+      for (int c = lane; c < n; c += 32) mine[c] += double(row[c]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n; c += RED_THREADS) {
+    double acc = 0;
+    for (int ww = 0; ww < warps; ++ww) acc += sm[ww * n + c];
+    partial[int64_t(blockIdx.x) * 2 * n + c] = acc;
+    partial[int64_t(blockIdx.x) * 2 * n + n + c] = 0.0;
+  }
+}
+
 int reduce_grid(int64_t m) {
   const int64_t want = (m + 63) / 64;
   const int64_t cap = int64_t(sm_count()) * 4;
@@ -171,9 +197,18 @@ extern "C" int pc_col_stats(const float* x, int64_t m, int n, int64_t ldx, doubl
 }
 
 extern "C" int pc_col_sum_unselected(const float* x, int64_t m, int n, int64_t ldx, const int64_t* rowptr, double* sums, void* workspace,
-                                   size_t workspace_bytes, pc_stream_t stream) {
-  PC_REQUIRE(rowptr, PC_ERR_INVALID, "col_sum_unselected: null rowptr");
-  return col_reduce<2>(x, ldx, nullptr, 4, m, n, nullptr, nullptr, rowptr, sums, workspace, workspace_bytes, as_stream(stream));
+                                     size_t workspace_bytes, pc_stream_t stream) {
+  PC_REQUIRE(rowptr && x && sums && workspace, PC_ERR_INVALID, "col_sum_unselected: null pointer");
+  PC_REQUIRE(m > 0 && n >= 1 && n <= 1024, PC_ERR_UNSUPPORTED, "col_sum_unselected: bad shape m=%lld n=%d", (long long)m, n);
+  const int grid = reduce_grid(m);
+  PC_REQUIRE(workspace_bytes >= size_t(grid) * 2 * n * sizeof(double), PC_ERR_WORKSPACE, "col_sum_unselected: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  col_sum_unselected_kernel<<<grid, RED_THREADS, size_t(RED_THREADS / 32) * n * sizeof(double), st>>>(x, ldx, m, n, rowptr,
+                                                                                                      reinterpret_cast<double*>(workspace));
+  PC_LAUNCH_CHECK();
+  col_reduce_final_kernel<<<(2 * n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, 2 * n, sums);
+  PC_LAUNCH_CHECK();
+  return PC_OK;
 }
 
 extern "C" int pc_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* x, int64_t ldx, int64_t m, int n,
