@@ -301,6 +301,7 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
     if (end > beg) {
       const float4 k = ldg4(KV + j * KV4 + lane);
       const float4 v = ldg4(KV + j * KV4 + ROW4 + lane);
+      const float4 k2 = scale4(k, scale_log2e);              // the logit scale applied once per column instead of once per edge
       for (int base = beg; base < end; base += 32) {
         const int cnt = min(32, end - base);
         uint32_t my_keep = 0;
@@ -324,8 +325,7 @@ gat_bwd_src_kernel(const float4* __restrict__ Q, const float4* __restrict__ KV, 
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             if (t + u < cnt) {
-              const float4 q2 = scale4(qi[u], scale_log2e);
-              const float s2 = group_sum<G>(dot4(q2, k));
+              const float s2 = group_sum<G>(dot4(qi[u], k2));
               const float p = exp2f(s2 - lse2[u]);
               float da = group_sum<G>(dot4(gi[u], v));
               float pk = p;
@@ -425,7 +425,7 @@ int check_common(const void* a, const void* b, const void* c, const void* d, int
     default: { constexpr int H = 8; constexpr bool DROP = DROPV; CALL; } break; \
   }
 
-constexpr int RU_FWD = 3, RU_DST = 3, RU_SRC = 2;   // edges per arithmetic batch in the ring kernels (data is already in shared memory)
+constexpr int RU_FWD = 3, RU_DST = 3, RU_SRC = 3;   // edges per arithmetic batch in the ring kernels (data is already in shared memory)
 
 }  // namespace
 }  // namespace pc

@@ -134,9 +134,10 @@ col_sum_unselected_kernel(const float* __restrict__ x, int64_t ldx, int64_t m, i
   double* mine = sm + w * n;
   for (int c = lane; c < n; c += 32) mine[c] = 0.0;
   __syncwarp();
-  const int64_t rows_per_cta = (ceil_div(m, int64_t(gridDim.x)) + 31) / 32 * 32;
-  const int64_t r_beg = int64_t(blockIdx.x) * rows_per_cta, r_end = min(m, r_beg + rows_per_cta);
-  for (int64_t base = r_beg + int64_t(w) * 32; base < r_end; base += int64_t(warps) * 32) {
+  // 32-row blocks are dealt round-robin over all warps of the grid: isolated nodes tend to cluster (the tail of a src < dst
+  // graph), a contiguous slab per CTA would leave all of them to a few CTAs.  The assignment is fixed: deterministic.
+  const int64_t r_end = m;
+  for (int64_t base = (int64_t(blockIdx.x) * warps + w) * 32; base < r_end; base += int64_t(gridDim.x) * warps * 32) {
     const int64_t r = base + lane;
     uint32_t empty = __ballot_sync(FULL, r < r_end && rowptr[r + 1] == rowptr[r]);
     while (empty) {
