@@ -319,11 +319,18 @@ int pc_rows_segment_sum(const float* rows, const int64_t* rowptr, const int32_t*
 
 /* The same as ONE call from an index list: out[n_rows, width] = dense gradient of table[index] given the gradient rows
  * [slots, width] (slot s belongs to table row index[s]); keys index << 32 | slot, stable radix sort on the row bytes,
- * CSR, pc_rows_segment_sum.  Replaces the atomicAdd-based backward of nn.Embedding / advanced indexing
+ * CSR, pc_rows_segment_sum; every output row is multiplied by scale[0] (device scalar, may be NULL).  Replaces the atomicAdd-based backward of nn.Embedding / advanced indexing
  * (p_companion.py:54,66; product2vec.py:132-134 on a shared table) with a deterministic one. */
 size_t pc_rows_index_grad_workspace_bytes(int64_t slots, int64_t n_rows);
-int pc_rows_index_grad(const float* rows, const int64_t* index, int64_t slots, int64_t n_rows, int width, float* out,
-                       void* workspace, size_t workspace_bytes, pc_stream_t stream);
+int pc_rows_index_grad(const float* rows, const int64_t* index, int64_t slots, int64_t n_rows, int width, const float* scale,
+                       float* out, void* workspace, size_t workspace_bytes, pc_stream_t stream);
+/* Triplet hinge (product2vec.py:137-154) on rows of ONE table picked by index: slot_rows int64 [(2 + kneg) batch] =
+ * anchors | positives | negatives (negative k of triplet b at 2 batch + b kneg + k).  Reads the rows straight from the
+ * table (no gathered copy); per_row [batch], loss = mean; slot_grads [(2 + kneg) batch, dim] (may be NULL) receives the
+ * gradient row of every slot for an upstream gradient of ONE - pc_rows_index_grad with scale = the upstream gradient
+ * then gives d_table.  dim % 4 == 0, dim <= 512. */
+int pc_triplet_indexed(const float* table, const int64_t* slot_rows, int64_t batch, int kneg, int dim, float margin, float eps,
+                       float* per_row, float* loss, float* slot_grads, pc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -73,7 +73,8 @@ PROTOTYPES = {
     "pc_rows_reduce_peers": (c_int, [P, P, c_int, c_int64, c_int, P, P]),
     "pc_halo_push": (c_int, [P, c_int64, P, c_int, P, P, P, P, c_int64, c_int, P]),
     "pc_rows_index_grad_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "pc_rows_index_grad": (c_int, [P, P, c_int64, c_int64, c_int, P, P, c_size_t, P]),
+    "pc_rows_index_grad": (c_int, [P, P, c_int64, c_int64, c_int, P, P, P, c_size_t, P]),
+    "pc_triplet_indexed": (c_int, [P, P, c_int64, c_int, c_int, c_float, c_float, P, P, P, P]),
     "pc_rows_segment_sum": (c_int, [P, P, P, c_int64, c_int, P, P]),
 }
 

@@ -63,10 +63,11 @@ rows_scatter_add_kernel(const float4* __restrict__ rows, const int64_t* __restri
 // the deterministic transpose of a row gather (gradient of table[index] without float atomics).
 __global__ void __launch_bounds__(256)
 rows_segment_sum_kernel(const float4* __restrict__ rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                        int64_t n, int width4, float4* __restrict__ out) {
+                        int64_t n, int width4, const float* __restrict__ scale, float4* __restrict__ out) {
   const int64_t r = int64_t(blockIdx.x) * 8 + warp_id();
   if (r >= n) return;
   const int64_t beg = rowptr[r], end = rowptr[r + 1];
+  const float sc = scale ? scale[0] : 1.f;
   for (int c = lane_id(); c < width4; c += 32) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t e = beg; e < end; ++e) {
@@ -217,15 +218,20 @@ extern "C" int pc_rows_scatter_add(const float* rows, const int64_t* index, int6
   return PC_OK;
 }
 
+static int segment_sum_scaled(const float* rows, const int64_t* rowptr, const int32_t* col, int64_t n, int width, const float* scale,
+                              float* out, pc_stream_t stream) {
+  rows_segment_sum_kernel<<<unsigned(ceil_div(n, 8)), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(rows), rowptr, col, n, width / 4, scale, reinterpret_cast<float4*>(out));
+  PC_LAUNCH_CHECK();
+  return PC_OK;
+}
+
 extern "C" int pc_rows_segment_sum(const float* rows, const int64_t* rowptr, const int32_t* col, int64_t n, int width,
                                    float* out, pc_stream_t stream) {
   PC_REQUIRE(n >= 0 && width > 0 && width % 4 == 0, PC_ERR_INVALID, "rows_segment_sum: bad n=%lld width=%d", (long long)n, width);
   if (n == 0) return PC_OK;
   PC_REQUIRE(rowptr && out, PC_ERR_INVALID, "rows_segment_sum: null pointer");
-  rows_segment_sum_kernel<<<unsigned(ceil_div(n, 8)), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(rows), rowptr, col, n, width / 4, reinterpret_cast<float4*>(out));
-  PC_LAUNCH_CHECK();
-  return PC_OK;
+  return segment_sum_scaled(rows, rowptr, col, n, width, nullptr, out, stream);
 }
 
 
@@ -237,8 +243,8 @@ extern "C" size_t pc_rows_index_grad_workspace_bytes(int64_t slots, int64_t n_ro
          align_up(size_t(n_rows + 1) * 8, 256) + align_up(size_t(slots) * 4, 256);
 }
 
-extern "C" int pc_rows_index_grad(const float* rows, const int64_t* index, int64_t slots, int64_t n_rows, int width, float* out,
-                                  void* workspace, size_t workspace_bytes, pc_stream_t stream) {
+extern "C" int pc_rows_index_grad(const float* rows, const int64_t* index, int64_t slots, int64_t n_rows, int width, const float* scale,
+                                  float* out, void* workspace, size_t workspace_bytes, pc_stream_t stream) {
   PC_REQUIRE(slots >= 0 && n_rows >= 0 && n_rows < (int64_t(1) << 31) && slots < (int64_t(1) << 31), PC_ERR_INVALID,
              "rows_index_grad: bad sizes");
   PC_REQUIRE(width > 0 && width % 4 == 0, PC_ERR_INVALID, "rows_index_grad: bad width=%d", width);
@@ -264,5 +270,5 @@ extern "C" int pc_rows_index_grad(const float* rows, const int64_t* index, int64
     if ((uint64_t(n_rows > 1 ? n_rows - 1 : 1) >> (8 * b)) != 0) mask |= 1u << (4 + b);
   if (int rc = pc_sort_keys(keys, slots, mask, sort_ws, sort_bytes, stream)) return rc;
   if (int rc = pc_csr_from_sorted_keys(keys, slots, n_rows, rowptr, col, stream)) return rc;
-  return pc_rows_segment_sum(rows, rowptr, col, n_rows, width, out, stream);
+  return segment_sum_scaled(rows, rowptr, col, n_rows, width, scale, out, stream);
 }

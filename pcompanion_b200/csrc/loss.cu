@@ -104,6 +104,68 @@ hinge_rows_bwd_kernel(const float4* __restrict__ A, const float4* __restrict__ P
   }
 }
 
+// Triplet hinge on rows of ONE table picked by index, forward and (unscaled) gradient rows in one pass: warp b reads
+// a = T[idx[b]], p = T[idx[B + b]], n_k = T[idx[2B + b K + k]] straight from the table (no gathered copy), writes the hinge of
+// triplet b and - when `grads` is given - the gradient rows of its 2 + K slots for an upstream gradient of ONE
+// (d loss / d slot row; the scalar upstream gradient is applied by the segment sum that builds d_table).  Same
+// arithmetic as hinge_rows_fwd / hinge_rows_bwd, the anchor gradient accumulated in registers.
+constexpr int TRI_MAXC = 4;   // float4 per lane: dim <= 512
+__global__ void __launch_bounds__(256)
+triplet_indexed_kernel(const float4* __restrict__ T, const int64_t* __restrict__ idx, int64_t batch, int kneg, int dim4,
+                       float margin, float eps, float* __restrict__ per_row, float4* __restrict__ grads) {
+  const int64_t b = int64_t(blockIdx.x) * 8 + warp_id();
+  if (b >= batch) return;
+  const int lane = lane_id();
+  const float4* a = T + idx[b] * dim4;
+  const float4* p = T + idx[batch + b] * dim4;
+  const int64_t n0 = 2 * batch + b * kneg;
+  const float dpos = row_distance(a, p, dim4, eps);
+  float my_dneg = 0.f, dneg_sum = 0.f;  // lane k keeps ||a - n_k||
+  for (int k = 0; k < kneg; ++k) {
+    const float d = row_distance(a, T + idx[n0 + k] * dim4, dim4, eps);
+    if (lane == k) my_dneg = d;
+    dneg_sum += d;
+  }
+  const float h = margin - dpos + dneg_sum / float(kneg);
+  if (lane == 0) per_row[b] = fmaxf(h, 0.f);
+  if (!grads) return;
+  const float gscale = h > 0.f ? 1.f / float(batch) : 0.f;
+  const float wpos = dpos > 0.f ? gscale / dpos : 0.f;  // torch.norm backward: 0 at norm == 0
+  float4 da[TRI_MAXC];
+#pragma unroll
+  for (int i = 0; i < TRI_MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < dim4) {
+      const float4 x = ldg4(a + c), y = ldg4(p + c);
+      const float4 up = make_float4((x.x - y.x + eps) * wpos, (x.y - y.y + eps) * wpos, (x.z - y.z + eps) * wpos,
+                                    (x.w - y.w + eps) * wpos);
+      grads[(batch + b) * dim4 + c] = up;
+      da[i] = make_float4(-up.x, -up.y, -up.z, -up.w);
+    }
+  }
+  for (int k = 0; k < kneg; ++k) {
+    const float dk = __shfl_sync(FULL, my_dneg, k);
+    const float wneg = dk > 0.f ? gscale / (dk * float(kneg)) : 0.f;
+    const float4* nk = T + idx[n0 + k] * dim4;
+#pragma unroll
+    for (int i = 0; i < TRI_MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < dim4) {
+        const float4 x = ldg4(a + c), y = ldg4(nk + c);
+        const float4 un = make_float4((x.x - y.x + eps) * wneg, (x.y - y.y + eps) * wneg, (x.z - y.z + eps) * wneg,
+                                      (x.w - y.w + eps) * wneg);
+        da[i].x += un.x; da[i].y += un.y; da[i].z += un.z; da[i].w += un.w;
+        grads[(n0 + k) * dim4 + c] = make_float4(-un.x, -un.y, -un.z, -un.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TRI_MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < dim4) grads[b * dim4 + c] = da[i];
+  }
+}
+
 __global__ void hinge_type_fwd_kernel(const float* __restrict__ S, const int64_t* __restrict__ pos,
                                       const int64_t* __restrict__ neg, int64_t rows, int64_t n_types, float margin,
                                       float* __restrict__ per_row) {
@@ -188,6 +250,22 @@ extern "C" int pc_hinge_type_bwd(const float* sims, const int64_t* pos, const in
   PC_REQUIRE(sims && pos && neg && grad_loss && d_sims, PC_ERR_INVALID, "hinge_type_bwd: null pointer");
   hinge_type_bwd_kernel<<<unsigned(ceil_div(rows, 256)), 256, 0, as_stream(stream)>>>(sims, pos, neg, rows, n_types,
                                                                                        margin, grad_loss, d_sims);
+  PC_LAUNCH_CHECK();
+  return PC_OK;
+}
+
+extern "C" int pc_triplet_indexed(const float* table, const int64_t* slot_rows, int64_t batch, int kneg, int dim, float margin,
+                                  float eps, float* per_row, float* loss, float* slot_grads, pc_stream_t stream) {
+  PC_REQUIRE(batch > 0, PC_ERR_INVALID, "triplet_indexed: batch must be positive (mean of an empty batch is undefined)");
+  PC_REQUIRE(table && slot_rows && per_row && loss, PC_ERR_INVALID, "triplet_indexed: null pointer");
+  PC_REQUIRE(kneg >= 1 && kneg <= 32, PC_ERR_UNSUPPORTED, "triplet_indexed: kneg=%d outside [1,32]", kneg);
+  PC_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 128 * TRI_MAXC, PC_ERR_UNSUPPORTED, "triplet_indexed: dim=%d must be a multiple of 4 up to %d", dim,
+             128 * TRI_MAXC);
+  cudaStream_t st = as_stream(stream);
+  triplet_indexed_kernel<<<unsigned(ceil_div(batch, 8)), 256, 0, st>>>(reinterpret_cast<const float4*>(table), slot_rows, batch, kneg,
+                                                                      dim / 4, margin, eps, per_row, reinterpret_cast<float4*>(slot_grads));
+  PC_LAUNCH_CHECK();
+  mean_kernel<<<1, 1024, 0, st>>>(per_row, batch, loss);
   PC_LAUNCH_CHECK();
   return PC_OK;
 }

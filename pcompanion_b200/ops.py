@@ -504,15 +504,16 @@ class _HingeRows(torch.autograd.Function):
         return da, dp, dn, None, None, None, None
 
 
-def index_rows_grad(rows: torch.Tensor, index: torch.Tensor, n_rows: int) -> torch.Tensor:
+def index_rows_grad(rows: torch.Tensor, index: torch.Tensor, n_rows: int, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Dense [n_rows, W] gradient of table[index] from the gradient rows [S, W], no float atomics (pc_rows_index_grad:
-    slots sorted stably by table row, summed per row in slot order)."""
+    slots sorted stably by table row, summed per row in slot order, times the device scalar `scale` if given)."""
     rows = rows.contiguous()
     index = index.reshape(-1).to(I64).contiguous()
     slots, w = rows.shape
     out = torch.empty(n_rows, w, dtype=F32, device=rows.device)
     ws = _lib.workspace(_lib.LIB.pc_rows_index_grad_workspace_bytes(slots, n_rows), rows.device)
-    call("pc_rows_index_grad", dev(rows, F32, "rows"), dev(index, I64, "index"), slots, n_rows, w, dev(out, F32, "out"),
+    call("pc_rows_index_grad", dev(rows, F32, "rows"), dev(index, I64, "index"), slots, n_rows, w,
+         dev(None if scale is None else scale.reshape(1).contiguous().to(F32), F32, "scale"), dev(out, F32, "out"),
          dev(ws, torch.uint8, "ws"), ws.numel(), stream())
     return out
 
@@ -542,37 +543,28 @@ def gather_rows(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
 
 
 class _TripletFromTable(torch.autograd.Function):
-    """Triplet hinge on rows of one embedding table selected by index (anchors | positives | negatives).
-    Backward returns a dense d_table built without float atomics: the slot list is stably sorted by node
-    (pc_sort_keys), turned into a CSR and summed per node in slot order (pc_rows_segment_sum)."""
+    """Triplet hinge on rows of one embedding table selected by index (anchors | positives | negatives), ONE kernel for
+    the loss and the gradient rows of all slots (pc_triplet_indexed reads the table through the index: no gathered copy,
+    no second pass in backward).  Backward returns a dense d_table built without float atomics: the slot list is stably
+    sorted by node, turned into a CSR and summed per node in slot order, times the upstream gradient (pc_rows_index_grad)."""
 
     @staticmethod
     def forward(ctx, table, slot_nodes, batch: int, kneg: int, margin: float, eps: float):
         table = table.contiguous()
-        rows = rows_gather(table, slot_nodes)                       # [(2 + kneg) * batch, D]
         d = table.shape[1]
         per = torch.empty(batch, dtype=F32, device=table.device)
         loss = torch.empty((), dtype=F32, device=table.device)
-        a, p, n = rows[:batch], rows[batch: 2 * batch], rows[2 * batch:]
-        call("pc_hinge_rows_fwd", dev(a, F32, "a"), dev(p, F32, "p"), dev(n, F32, "n"), batch, 1, kneg, d, margin, eps,
-             dev(per, F32, "per"), dev(loss, F32, "loss"), stream())
-        ctx.save_for_backward(rows, slot_nodes)
-        ctx.cfg = (batch, kneg, margin, eps, table.shape[0])
+        grads = torch.empty(slot_nodes.numel(), d, dtype=F32, device=table.device) if ctx.needs_input_grad[0] else None
+        call("pc_triplet_indexed", dev(table, F32, "table"), dev(slot_nodes, I64, "slot_rows"), batch, kneg, d, margin, eps,
+             dev(per, F32, "per"), dev(loss, F32, "loss"), dev(grads, F32, "slot_grads"), stream())
+        ctx.save_for_backward(grads, slot_nodes)
+        ctx.n_nodes = table.shape[0]
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        rows, slot_nodes = ctx.saved_tensors
-        batch, kneg, margin, eps, n_nodes = ctx.cfg
-        d = rows.shape[1]
-        g = g.contiguous().to(F32)
-        grads = torch.empty_like(rows)
-        a, p, n = rows[:batch], rows[batch: 2 * batch], rows[2 * batch:]
-        call("pc_hinge_rows_bwd", dev(a, F32, "a"), dev(p, F32, "p"), dev(n, F32, "n"), batch, 1, kneg, d, margin, eps,
-             dev(g, F32, "grad"), dev(grads[:batch], F32, "da"), dev(grads[batch: 2 * batch], F32, "dp"),
-             dev(grads[2 * batch:], F32, "dn"), stream())
-        d_table = index_rows_grad(grads, slot_nodes, n_nodes)
-        return d_table, None, None, None, None, None
+        grads, slot_nodes = ctx.saved_tensors
+        return index_rows_grad(grads, slot_nodes, ctx.n_nodes, scale=g), None, None, None, None, None
 
 
 def triplet_hinge_indexed(table: torch.Tensor, anchor_idx: torch.Tensor, positive_idx: torch.Tensor,
