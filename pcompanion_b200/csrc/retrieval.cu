@@ -57,7 +57,11 @@ __device__ __forceinline__ void warp_topk_insert(Cand& mine, int k, double s, in
 constexpr int RB = 8;            // score rows per group
 constexpr int DCH = 32;          // dims per staged chunk
 constexpr int TILE_LD = 36;      // floats per staged product chunk (32 + 4 pad: conflict-free LDS.128 across lanes)
-constexpr int TILE_FLOATS = 32 * TILE_LD;
+constexpr int PP = 2;            // products per lane: every q value fetched from shared memory feeds PP fp64 chains.  With one
+                                 // product per lane the kernel was bound by the shared-memory pipe (ncu: 0.73 LSU wavefronts
+                                 // per SM cycle, fp64 pipe 24 % busy): 16 broadcast loads of q per 32 fp64 FMAs.
+constexpr int BATCH = 32 * PP;   // products per warp per pass
+constexpr int TILE_FLOATS = BATCH * TILE_LD;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
@@ -65,29 +69,30 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
 }
 
-// stage the 32-dim chunk `d0` of the warp's 32 products: 8 lanes cover the 128-byte piece of one product
-__device__ __forceinline__ void stage_chunk(float* tile, const float* __restrict__ catalog, int dim, int d0, int member) {
+// stage the 32-dim chunk `d0` of the warp's BATCH products (product p < 32: lane p's member[0], else lane p - 32's member[1]):
+// 8 lanes cover the 128-byte piece of one product
+__device__ __forceinline__ void stage_chunk(float* tile, const float* __restrict__ catalog, int dim, int d0, const int (&member)[PP]) {
   const int lane = lane_id();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < BATCH / 4; ++j) {
     const int prod = j * 4 + (lane >> 3);
-    const int m = __shfl_sync(FULL, member, prod);
+    const int m = __shfl_sync(FULL, member[prod >> 5], prod & 31);
     const float* src = catalog + (m >= 0 ? int64_t(m) * dim + d0 + (lane & 7) * 4 : 0);
     cp_async16(tile + prod * TILE_LD + (lane & 7) * 4, src, m >= 0);
   }
 }
 
 // grid = (splits, n_groups).  Group g = score rows row_ids[grp_begin[g] .. grp_begin[g+1]) (<= RB), all ranking
-// members[seg_begin[g] .. seg_end[g]).  Lane = one product of a 32-product batch; 32-dim chunks are staged
-// through shared memory with cp.async (double-buffered, coalesced), then every lane advances RB independent
-// sequential fp64 dot products (the RB chains interleave, which is what keeps the fp64 pipe busy).
+// members[seg_begin[g] .. seg_end[g]).  A lane owns PP products of a BATCH-product pass; 32-dim chunks are staged
+// through shared memory with cp.async (double-buffered, coalesced), then every lane advances PP x RB independent
+// sequential fp64 dot products (the chains interleave, which is what keeps the fp64 pipe busy).
 __device__ __forceinline__ void topk_group_body(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
                                                 const int32_t* __restrict__ members, const int32_t* __restrict__ row_ids,
                                                 int r_beg, int n_rows, int64_t beg, int64_t end, int k, int splits, int split,
                                                 int64_t index_base, double* __restrict__ part_s, int64_t* __restrict__ part_i) {
   extern __shared__ double smem_d[];
   double* q_s = smem_d;                                                      // [RB][dim], rows >= n_rows are zero
-  float* tiles = reinterpret_cast<float*>(q_s + RB * dim);                   // [TK_WARPS][2][32][TILE_LD]
+  float* tiles = reinterpret_cast<float*>(q_s + RB * dim);                   // [TK_WARPS][2][BATCH][TILE_LD]
   Cand* lists = reinterpret_cast<Cand*>(tiles + TK_WARPS * 2 * TILE_FLOATS); // [TK_WARPS][RB][32]
   const int lane = lane_id(), w = warp_id();
   for (int i = threadIdx.x; i < RB * dim; i += blockDim.x) {
@@ -106,17 +111,22 @@ __device__ __forceinline__ void topk_group_body(const float* __restrict__ Q, int
   const int n_chunks = dim / DCH;
   auto member_at = [&](int64_t pos) -> int { return pos < se ? (members ? members[pos] : int(pos)) : -1; };
 
-  int64_t base = sb + int64_t(w) * 32;
-  int cur = member_at(base + lane);
+  int64_t base = sb + int64_t(w) * BATCH;
+  int cur[PP], nxt[PP];
+#pragma unroll
+  for (int pp = 0; pp < PP; ++pp) cur[pp] = member_at(base + 32 * pp + lane);
   int buf = 0;
   if (base < se) stage_chunk(tile, catalog, dim, 0, cur);
   asm volatile("cp.async.commit_group;" ::: "memory");
   while (base < se) {
-    const int64_t next_base = base + TK_WARPS * 32;
-    const int nxt = member_at(next_base + lane);
-    double acc[RB];
+    const int64_t next_base = base + TK_WARPS * BATCH;
 #pragma unroll
-    for (int r = 0; r < RB; ++r) acc[r] = 0.0;
+    for (int pp = 0; pp < PP; ++pp) nxt[pp] = member_at(next_base + 32 * pp + lane);
+    double acc[PP][RB];
+#pragma unroll
+    for (int pp = 0; pp < PP; ++pp)
+#pragma unroll
+      for (int r = 0; r < RB; ++r) acc[pp][r] = 0.0;
     for (int c = 0; c < n_chunks; ++c) {
       if (c + 1 < n_chunks) stage_chunk(tile + (buf ^ 1) * TILE_FLOATS, catalog, dim, (c + 1) * DCH, cur);
       else if (next_base < se) stage_chunk(tile + (buf ^ 1) * TILE_FLOATS, catalog, dim, 0, nxt);
@@ -126,42 +136,49 @@ __device__ __forceinline__ void topk_group_body(const float* __restrict__ Q, int
       const float* mine_c = tile + buf * TILE_FLOATS + lane * TILE_LD;
       const double* qq = q_s + c * DCH;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        double cd[DCH / 2];
+      for (int j = 0; j < DCH / 4; ++j) {            // four dims at a time: PP x 4 converted values live in registers
+        double cd[PP][4];
 #pragma unroll
-        for (int j = 0; j < DCH / 8; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(mine_c + half * (DCH / 2) + 4 * j);
-          cd[4 * j] = double(v.x); cd[4 * j + 1] = double(v.y); cd[4 * j + 2] = double(v.z); cd[4 * j + 3] = double(v.w);
+        for (int pp = 0; pp < PP; ++pp) {
+          const float4 v = *reinterpret_cast<const float4*>(mine_c + pp * 32 * TILE_LD + 4 * j);
+          cd[pp][0] = double(v.x); cd[pp][1] = double(v.y); cd[pp][2] = double(v.z); cd[pp][3] = double(v.w);
         }
 #pragma unroll
-        for (int dd = 0; dd < DCH / 2; dd += 2) {
+        for (int dd = 0; dd < 4; dd += 2) {
 #pragma unroll
-          for (int r = 0; r < RB; ++r) {   // RB independent accumulation chains, each sequential in d
-            const double2 q2 = *reinterpret_cast<const double2*>(qq + r * dim + half * (DCH / 2) + dd);
-            acc[r] = fma(q2.x, cd[dd], acc[r]);
-            acc[r] = fma(q2.y, cd[dd + 1], acc[r]);
+          for (int r = 0; r < RB; ++r) {   // PP x RB independent accumulation chains, each sequential in d
+            const double2 q2 = *reinterpret_cast<const double2*>(qq + r * dim + 4 * j + dd);
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp) {
+              acc[pp][r] = fma(q2.x, cd[pp][dd], acc[pp][r]);
+              acc[pp][r] = fma(q2.y, cd[pp][dd + 1], acc[pp][r]);
+            }
           }
         }
       }
       __syncwarp();
       buf ^= 1;
     }
-    const int64_t gidx = cur >= 0 ? int64_t(cur) + index_base : -1;
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      if (r < n_rows) {
-        const double thr_s = shfl_d(mine[r].s, k - 1);
-        const int64_t thr_i = shfl_i64(mine[r].i, k - 1);
-        uint32_t cand = __ballot_sync(FULL, gidx >= 0 && ranks_before(acc[r], gidx, thr_s, thr_i));
-        while (cand) {
-          const int src = __ffs(cand) - 1;
-          cand &= cand - 1;
-          warp_topk_insert(mine[r], k, shfl_d(acc[r], src), shfl_i64(gidx, src));
+    for (int pp = 0; pp < PP; ++pp) {
+      const int64_t gidx = cur[pp] >= 0 ? int64_t(cur[pp]) + index_base : -1;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (r < n_rows) {
+          const double thr_s = shfl_d(mine[r].s, k - 1);
+          const int64_t thr_i = shfl_i64(mine[r].i, k - 1);
+          uint32_t cand = __ballot_sync(FULL, gidx >= 0 && ranks_before(acc[pp][r], gidx, thr_s, thr_i));
+          while (cand) {
+            const int src = __ffs(cand) - 1;
+            cand &= cand - 1;
+            warp_topk_insert(mine[r], k, shfl_d(acc[pp][r], src), shfl_i64(gidx, src));
+          }
         }
       }
     }
     base = next_base;
-    cur = nxt;
+#pragma unroll
+    for (int pp = 0; pp < PP; ++pp) cur[pp] = nxt[pp];
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
@@ -345,8 +362,8 @@ extern "C" int pc_topk_groups(const float* q, int64_t rows, int dim, const float
   cudaStream_t st = as_stream(stream);
   const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 2 * TILE_FLOATS * sizeof(float) +
                       size_t(TK_WARPS) * RB * 32 * sizeof(Cand);
-  PC_CUDA(cudaFuncSetAttribute(topk_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  PC_REQUIRE(smem <= 160 * 1024, PC_ERR_UNSUPPORTED, "topk_groups: shared memory budget exceeded");
+  PC_CUDA(cudaFuncSetAttribute(topk_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PC_REQUIRE(smem <= 200 * 1024, PC_ERR_UNSUPPORTED, "topk_groups: shared memory budget exceeded");
   double* ps = out_scores;
   int64_t* pi = out_idx;
   if (splits > 1) {
@@ -403,8 +420,8 @@ extern "C" int pc_topk_by_type(const float* q, int64_t rows, int dim, const floa
   PC_LAUNCH_CHECK();
   const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 2 * TILE_FLOATS * sizeof(float) +
                       size_t(TK_WARPS) * RB * 32 * sizeof(Cand);
-  PC_REQUIRE(smem <= 160 * 1024, PC_ERR_UNSUPPORTED, "topk_by_type: shared memory budget exceeded");
-  PC_CUDA(cudaFuncSetAttribute(topk_planned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  PC_REQUIRE(smem <= 200 * 1024, PC_ERR_UNSUPPORTED, "topk_by_type: shared memory budget exceeded");
+  PC_CUDA(cudaFuncSetAttribute(topk_planned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   double* ps = out_scores;
   int64_t* pi = out_idx;
   if (splits > 1) {
