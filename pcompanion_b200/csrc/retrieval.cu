@@ -14,6 +14,8 @@
 // at a time, so a catalog row is fetched once per group instead of once per score row.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pc {
@@ -55,8 +57,8 @@ __device__ __forceinline__ void warp_topk_insert(Cand& mine, int k, double s, in
 }
 
 constexpr int RB = 8;            // score rows per group
-constexpr int DCH = 32;          // dims per staged chunk
-constexpr int TILE_LD = 36;      // floats per staged product chunk (32 + 4 pad: conflict-free LDS.128 across lanes)
+constexpr int DCH = 16;          // dims per staged chunk
+constexpr int TILE_LD = 20;      // floats per staged product chunk (16 + 4 pad: conflict-free LDS.128 across lanes)
 constexpr int PP = 2;            // products per lane: every q value fetched from shared memory feeds PP fp64 chains.  With one
                                  // product per lane the kernel was bound by the shared-memory pipe (ncu: 0.73 LSU wavefronts
                                  // per SM cycle, fp64 pipe 24 % busy): 16 broadcast loads of q per 32 fp64 FMAs.
@@ -69,16 +71,16 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
 }
 
-// stage the 32-dim chunk `d0` of the warp's BATCH products (product p < 32: lane p's member[0], else lane p - 32's member[1]):
-// 8 lanes cover the 128-byte piece of one product
+// stage the DCH-dim chunk `d0` of the warp's BATCH products (product p < 32: lane p's member[0], else lane p - 32's member[1]):
+// 4 lanes cover the 64-byte piece of one product
 __device__ __forceinline__ void stage_chunk(float* tile, const float* __restrict__ catalog, int dim, int d0, const int (&member)[PP]) {
   const int lane = lane_id();
 #pragma unroll
-  for (int j = 0; j < BATCH / 4; ++j) {
-    const int prod = j * 4 + (lane >> 3);
+  for (int j = 0; j < BATCH / 8; ++j) {
+    const int prod = j * 8 + (lane >> 2);
     const int m = __shfl_sync(FULL, member[prod >> 5], prod & 31);
-    const float* src = catalog + (m >= 0 ? int64_t(m) * dim + d0 + (lane & 7) * 4 : 0);
-    cp_async16(tile + prod * TILE_LD + (lane & 7) * 4, src, m >= 0);
+    const float* src = catalog + (m >= 0 ? int64_t(m) * dim + d0 + (lane & 3) * 4 : 0);
+    cp_async16(tile + prod * TILE_LD + (lane & 3) * 4, src, m >= 0);
   }
 }
 
@@ -93,7 +95,7 @@ __device__ __forceinline__ void topk_group_body(const float* __restrict__ Q, int
   extern __shared__ double smem_d[];
   double* q_s = smem_d;                                                      // [RB][dim], rows >= n_rows are zero
   float* tiles = reinterpret_cast<float*>(q_s + RB * dim);                   // [TK_WARPS][2][BATCH][TILE_LD]
-  Cand* lists = reinterpret_cast<Cand*>(tiles + TK_WARPS * 2 * TILE_FLOATS); // [TK_WARPS][RB][32]
+  Cand* lists = reinterpret_cast<Cand*>(tiles);                              // [TK_WARPS][RB][32], reuses the tile area after the scan
   const int lane = lane_id(), w = warp_id();
   for (int i = threadIdx.x; i < RB * dim; i += blockDim.x) {
     const int r = i / dim, d = i - r * dim;
@@ -181,6 +183,7 @@ __device__ __forceinline__ void topk_group_body(const float* __restrict__ Q, int
     for (int pp = 0; pp < PP; ++pp) cur[pp] = nxt[pp];
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();                 // every warp is done with its tiles: the area becomes the candidate lists
 #pragma unroll
   for (int r = 0; r < RB; ++r) lists[(w * RB + r) * 32 + lane] = mine[r];
   __syncthreads();
@@ -202,7 +205,7 @@ __device__ __forceinline__ void topk_group_body(const float* __restrict__ Q, int
   }
 }
 
-__global__ void __launch_bounds__(TK_WARPS * 32)
+__global__ void __launch_bounds__(TK_WARPS * 32, 2)
 topk_groups_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
                    const int32_t* __restrict__ members, const int32_t* __restrict__ row_ids,
                    const int32_t* __restrict__ grp_begin, const int64_t* __restrict__ seg_begin,
@@ -248,7 +251,7 @@ __global__ void topk_plan_kernel(const uint64_t* __restrict__ keys, int64_t rows
   grp_rows[p] = n;
 }
 
-__global__ void __launch_bounds__(TK_WARPS * 32)
+__global__ void __launch_bounds__(TK_WARPS * 32, 2)
 topk_planned_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ catalog,
                     const int32_t* __restrict__ members, const int32_t* __restrict__ row_ids,
                     const int32_t* __restrict__ grp_rows, const uint64_t* __restrict__ keys,
@@ -360,8 +363,8 @@ extern "C" int pc_topk_groups(const float* q, int64_t rows, int dim, const float
   PC_REQUIRE(dim >= DCH && dim % DCH == 0 && dim <= 1024, PC_ERR_UNSUPPORTED, "topk_groups: dim=%d must be a multiple of %d (<= 1024)", dim, DCH);
   PC_REQUIRE(splits >= 1 && splits <= 65535, PC_ERR_UNSUPPORTED, "topk_groups: bad splits");
   cudaStream_t st = as_stream(stream);
-  const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 2 * TILE_FLOATS * sizeof(float) +
-                      size_t(TK_WARPS) * RB * 32 * sizeof(Cand);
+  const size_t smem = size_t(RB) * dim * sizeof(double) +
+                      std::max(size_t(TK_WARPS) * 2 * TILE_FLOATS * sizeof(float), size_t(TK_WARPS) * RB * 32 * sizeof(Cand));
   PC_CUDA(cudaFuncSetAttribute(topk_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   PC_REQUIRE(smem <= 200 * 1024, PC_ERR_UNSUPPORTED, "topk_groups: shared memory budget exceeded");
   double* ps = out_scores;
@@ -418,8 +421,8 @@ extern "C" int pc_topk_by_type(const float* q, int64_t rows, int dim, const floa
   if (int rc = pc_sort_keys(keys, rows, mask, sort_ws, sort_bytes, stream)) return rc;
   topk_plan_kernel<<<tb, 256, 0, st>>>(keys, rows, row_ids, grp_rows);
   PC_LAUNCH_CHECK();
-  const size_t smem = size_t(RB) * dim * sizeof(double) + size_t(TK_WARPS) * 2 * TILE_FLOATS * sizeof(float) +
-                      size_t(TK_WARPS) * RB * 32 * sizeof(Cand);
+  const size_t smem = size_t(RB) * dim * sizeof(double) +
+                      std::max(size_t(TK_WARPS) * 2 * TILE_FLOATS * sizeof(float), size_t(TK_WARPS) * RB * 32 * sizeof(Cand));
   PC_REQUIRE(smem <= 200 * 1024, PC_ERR_UNSUPPORTED, "topk_by_type: shared memory budget exceeded");
   PC_CUDA(cudaFuncSetAttribute(topk_planned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   double* ps = out_scores;
