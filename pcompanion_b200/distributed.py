@@ -3,13 +3,16 @@
 The reference has no multi-GPU path at all; this is new.  Rank g owns the contiguous node range
 [bounds[g], bounds[g+1]): their features, FFN outputs, Q and K|V rows, and every CSR row (edge
 list of an aggregating node) of those nodes.  Columns are global ids; the K|V rows of columns
-owned by other ranks form the halo.  Per step:
+owned by other ranks form the halo.  Three transports move it (the layer itself is fused.py):
 
-  forward   pack local K|V rows requested by peers (pc_rows_gather) -> all-to-all (NCCL over
-            NVLink, variable splits) -> GAT kernel over [local | halo] rows via a remapped CSR
-  backward  dK|dV partials of halo rows -> reverse all-to-all -> owner adds them in fixed peer
-            order (pc_rows_scatter_add: unique ids per peer => deterministic, no float atomics)
-  weights   replicated; gradients all-reduced (sum) before the optimiser step
+  DenseHalo  (partitions that need most remote rows, e.g. uniform random graphs): blocks of FFN outputs travel on the
+             copy engines and K|V is projected at the receiver; dK|dV blocks return per owner range; point-to-point
+             flags in symmetric memory order everything - no NCCL call on the data path
+  PeerHalo   (sparse halos): pc_halo_push gathers the requested K|V rows and stores them into the peers' tables over
+             NVLink; partials return per owner range on the copy engines
+  NCCL       all_to_all_single with variable splits, the fallback when symmetric memory is unavailable
+  backward   the owner adds the returned partials in fixed peer order (pc_rows_reduce_peers: deterministic, no atomics)
+  weights    replicated; gradients all-reduced (sum) before the optimiser step
 
 ``HaloPlan`` holds only index logic and the collectives, so it runs on any backend (the
 world_size-2 ``gloo`` tests drive it on CPU tensors); all row movement and arithmetic on the
