@@ -89,9 +89,10 @@ class HaloPlan:
         # remap columns: local -> [0, n_local), remote -> n_local + position in `remote`
         is_local = (col >= base) & (col < end)
         ext = torch.where(is_local, col - base, self.n_local + torch.searchsorted(remote, col))
-        # (hub splitting is a single-GPU feature so far: the per-owner column ranges of the backward are not split)
+        # hub ROWS (destinations with very many neighbours) are split as on one GPU; the src-major backward runs per owner
+        # range, where hub columns stay unsplit (a rank only holds its own share of a popular product's in-edges)
         self.graph = ops.CSRGraph(rowptr.contiguous(), ext.to(torch.int32).contiguous(), self.n_local,
-                                  self.n_local + self.n_halo, split_hubs=False) if (col.is_cuda and rowptr is not None) else None
+                                  self.n_local + self.n_halo) if (col.is_cuda and rowptr is not None) else None
         self.col_ext = ext
         self.rowptr = rowptr
         self.peer: Optional["PeerHalo"] = None
@@ -350,7 +351,7 @@ class DenseHalo:
         self._h_peer = [hh.get_buffer(p, (self.n_total, 128), torch.float32) if p != rank else None for p in range(world)]
         self._ret_peer = [hr.get_buffer(p, (world, self.n_loc_max, 256), torch.float32) if p != rank else None for p in range(world)]
         self.kv_all = torch.empty(self.n_total, 256, dtype=torch.float32, device=dev)
-        self.graph = ops.CSRGraph(plan.rowptr.contiguous(), plan.col_global, plan.n_local, self.n_total, split_hubs=False)
+        self.graph = ops.CSRGraph(plan.rowptr.contiguous(), plan.col_global, plan.n_local, self.n_total)
         self.graph.transposed()
         slot = torch.arange(plan.n_local, dtype=torch.int32, device=dev).unsqueeze(0) + \
             (torch.arange(world, dtype=torch.int32, device=dev) * self.n_loc_max).unsqueeze(1)

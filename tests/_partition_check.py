@@ -32,6 +32,7 @@ def check_partitioned(rank: int, world: int, dev: torch.device, n: int = 3000, r
     cuts = sorted(rng.choice(np.arange(200, n - 200), world - 1, replace=False).tolist()) if world > 1 else []
     bounds = [0] + cuts + [n]
     deg = rng.poisson(7, n); deg[::11] = 0
+    deg[5], deg[n - 7] = 700, 300            # hub rows (> ops.HUB_THRESHOLD neighbours): attended slice by slice and merged
     rowptr = np.zeros(n + 1, np.int64); np.cumsum(deg, out=rowptr[1:])
     col = np.concatenate([np.sort(rng.choice(n, d, replace=False)) for d in deg]).astype(np.int32)
     x = rng.normal(size=(n, 128)).astype(np.float32)
