@@ -194,3 +194,20 @@ def test_scalable_generator_chain_equals_the_oracle_chain_on_shared_uniforms():
         keys = (s.numpy().astype(np.int64) << 32) | d.numpy().astype(np.int64)
         assert np.array_equal(keys, np.asarray(ref[t]).astype(np.int64)), t
     assert 0.30 < ours["co_view"][0].numel() / src.size < 0.36          # 0.3 (x1.5 inside a category, 1/5 of the pairs)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: one JSON line with the contract's keys, timed on the host cores through the oracle port
+    (the one place besides tests / smoke where oracle/ may be executed)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "retrieval",
+                          "--steps", "1", "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "topk_queries_per_sec" and line["unit"] == "queries/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
