@@ -74,7 +74,7 @@ rows_segment_sum_kernel(const float4* __restrict__ rows, const int64_t* __restri
       const float4 v = ldg4(rows + int64_t(col[e]) * width4 + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    out[r * width4 + c] = acc;
+    out[r * width4 + c] = scale ? make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc) : acc;
   }
 }
 

@@ -660,6 +660,12 @@ def test_indexed_triplet_loss_equals_gathered_loss_and_is_deterministic():
     t3 = table.clone().requires_grad_(True)
     ops.triplet_hinge_indexed(t3, ai, pi, ni, 1.0).backward()
     assert torch.equal(t3.grad, t1.grad)                                       # no atomics: bit-reproducible
+    # a non-unit upstream gradient (the loss is scaled / is one term of a sum) reaches the table gradient
+    t4 = table.clone().requires_grad_(True)
+    (ops.triplet_hinge_indexed(t4, ai, pi, ni, 1.0) * -2.5).backward()
+    close(t4.grad, -2.5 * t2.grad.cpu().numpy(), what="d table, upstream gradient -2.5")
+    with torch.no_grad():
+        assert torch.equal(ops.triplet_hinge_indexed(table, ai, pi, ni, 1.0), l1.detach())   # forward only: no gradient rows
 
 
 def test_dense_tensor_core_retrieval_equals_exact_segmented_path():
