@@ -204,3 +204,37 @@ def test_graphed_train_step_equals_eager_steps_and_redraws_dropout():
     step = GraphedTrainStep(m, opt0, batches[0])
     seen = {float(step(batches[0])) for _ in range(4)}
     assert len(seen) == 4, f"dropout mask was not redrawn between replays: {seen}"
+
+
+def test_evaluate_model_matches_a_float64_restatement_of_the_reference_loop():
+    """Metrics.evaluate_model (metrics.py:62-117): in-batch scoring of the [3B, D] projections against the B targets on the
+    tcgen05 scoring kernel (B % 4 == 0) or the library GEMM (ragged last batch), Hit@{1,3,10}, diversity, relevance."""
+    from pcompanion_b200 import Metrics, PCompanion
+    g = torch.Generator().manual_seed(21)
+    t = 40
+    table = torch.randn(500, 128, generator=g)
+    torch.manual_seed(2)
+    model = PCompanion(make_cfg(NUM_TYPES=t), table).to(dev())
+
+    def batch(b):
+        return {"query_ids": torch.randint(0, 500, (b,), generator=g), "query_types": torch.randint(0, t, (b,), generator=g),
+                "positive_items": torch.randn(b, 128, generator=g), "target_features": torch.randn(b, 128, generator=g)}
+    loader = [batch(32), batch(30)]                                     # 30: not a multiple of 4 -> library GEMM path
+    got = Metrics.evaluate_model(model, loader, dev())
+    want = {"hit@1": 0.0, "hit@3": 0.0, "hit@10": 0.0, "type_diversity": 0.0, "mean_relevance": 0.0}
+    model.eval()
+    with torch.no_grad():
+        for bt in loader:
+            bt = {k: v.to(dev()) for k, v in bt.items()}
+            out = model(bt)
+            proj = out["projected_embeddings"].double()
+            sims = proj.reshape(-1, 128) @ bt["target_features"].double().T
+            gt = torch.arange(sims.size(0), device=dev())
+            for k in (1, 3, 10):
+                top = torch.sort(sims, dim=1, descending=True, stable=True).indices[:, :k]
+                want[f"hit@{k}"] += (top == gt.unsqueeze(1)).any(1).double().mean().item()
+            types = out["complementary_types"]
+            want["type_diversity"] += torch.unique(types, dim=1).size(1) / types.size(1)
+            want["mean_relevance"] += torch.cosine_similarity(proj, bt["positive_items"].double().unsqueeze(1), dim=-1).mean().item()
+    for k in want:
+        assert abs(got[k] - want[k] / len(loader)) < 1e-6, (k, got[k], want[k] / len(loader))
