@@ -358,9 +358,6 @@ class DenseHalo:
         slot[rank] = -1
         self.slot = slot.contiguous()
         self.side = torch.cuda.Stream(device=dev)
-        # forward copies: PC_DENSE_STREAMS=2 issues the rounds alternately on two streams (two copy engines at once)
-        n_fwd = max(1, int(os.environ.get("PC_DENSE_STREAMS", "1")))
-        self._fwd_streams = [self.side] + [torch.cuda.Stream(device=dev) for _ in range(n_fwd - 1)]
         self.version = 0
         npad = 2 * world
         self._pads = [[h.get_signal_pad(p, (npad,), torch.int32) if p != rank else None for p in range(world)] for h in (hh, hr)]
@@ -397,12 +394,10 @@ class DenseHalo:
         if self.version > 1:
             for k in range(1, world):
                 hh.wait_signal((rank + k) % world, self.CH_CONSUMED, self.SIGNAL_TIMEOUT_MS)
-        streams = self._fwd_streams
-        for st in streams:
-            st.wait_stream(torch.cuda.current_stream())
-        for k in range(1, world):
-            p = (rank + k) % world
-            with torch.cuda.stream(streams[(k - 1) % len(streams)]):
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            for k in range(1, world):
+                p = (rank + k) % world
                 with region("ce:h_block"):
                     self._h_peer[p][b0:b1].copy_(self.h_all[b0:b1])
                     self._flag(0, p, self.CH_LANDED)
