@@ -421,11 +421,19 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           // the four quarters are combined in fixed order into the CTA's float64 accumulators (pc_col_stats fused away)
           const int t128 = quad * 32 + lane, cc = t128 & 31, qtr = t128 >> 5;
           float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const int rw = qtr * 32 + rr;
-            if (int64_t(m0) + rw < p.m) {
-              const float v = lds32(out_addr + rw * 128 + ((((cc >> 2) ^ (rw & 7)) << 4) | ((cc & 3) << 2)));
+          const int64_t left = p.m - m0 - qtr * 32;           // rows of this quarter that exist (only the last tile is short)
+          const int valid = left >= 32 ? 32 : (left > 0 ? int(left) : 0);
+          const uint32_t col_off = uint32_t((cc & 3) << 2), chunk = uint32_t(cc >> 2);
+          if (valid == 32) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {                 // rw & 7 == rr & 7: the quarter starts at a multiple of 32
+              const float v = lds32(out_addr + uint32_t(qtr * 32 + rr) * 128 + (((chunk ^ uint32_t(rr & 7)) << 4) | col_off));
+              s1 += v;
+              s2 = fmaf(v, v, s2);
+            }
+          } else {
+            for (int rr = 0; rr < valid; ++rr) {
+              const float v = lds32(out_addr + uint32_t(qtr * 32 + rr) * 128 + (((chunk ^ uint32_t(rr & 7)) << 4) | col_off));
               s1 += v;
               s2 = fmaf(v, v, s2);
             }
