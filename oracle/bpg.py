@@ -7,7 +7,7 @@ compared bit-exactly with the device CSR.
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Set, Tuple
+from typing import Dict, Set, Tuple
 
 import numpy as np
 

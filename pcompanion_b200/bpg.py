@@ -15,7 +15,7 @@ Large graphs skip the Python dict/set surface entirely via ``from_arrays``.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Iterable, List, Optional, Set, Tuple
+from typing import Any, Dict, List, Optional, Set, Tuple
 
 import torch
 

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 from torch.utils.data import Dataset
 
-from . import _lib, ops
+from . import ops
 from ._lib import call, dev, stream
 from .bpg import BehaviorProductGraph
 

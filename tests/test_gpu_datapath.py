@@ -1,7 +1,6 @@
 """GPU tests of the data path: drop-in datasets over the device CSR, device negative sampler,
 drop-in training loop, recommendation entry point, and C4-scale retrieval properties."""
 import random
-from types import SimpleNamespace
 
 import numpy as np
 import pytest
